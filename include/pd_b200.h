@@ -1,0 +1,209 @@
+/*
+ * pd_b200.h — C ABI of libpd_b200.so: hand-written sm_100a kernels behind the PyDreamer
+ * world-model training step + imagination rollout (BASELINE.json north_star).
+ *
+ * The reference (jurgisp/pydreamer) has no FFI: its boundary is the Python class
+ * pydreamer.models.Dreamer (pydreamer/models/dreamer.py:19).  These entry points are the
+ * arithmetic that class performs, one per fused device op; pydreamer_b200/dreamer.py composes
+ * them behind the reference's Dreamer API.  Each declaration cites the reference lines whose
+ * math it replaces.
+ *
+ * Conventions:
+ *   - plain pointers/sizes only; every pointer is a DEVICE pointer to fp32 unless noted;
+ *   - `ld*` are row strides in ELEMENTS, so callers can pass views into concatenated buffers;
+ *   - never allocates device memory, never synchronises, enqueues on `stream` (a cudaStream_t);
+ *   - returns 0 on success, a negative PD_ERR_* otherwise; pd_last_error() gives the message;
+ *   - one handle per (process, device); a handle is not re-entrant.
+ */
+#ifndef PD_B200_H
+#define PD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pd_handle pd_handle;
+
+#define PD_OK 0
+#define PD_ERR_ARG (-1)
+#define PD_ERR_LAUNCH (-2)
+#define PD_ERR_DEVICE (-3)
+#define PD_ERR_UNSUPPORTED (-4)
+
+#define PD_ACT_NONE 0
+#define PD_ACT_ELU 1
+
+#define PD_GEMM_TCGEN05 0 /* tcgen05.mma kind::tf32 + TMA + TMEM (default, the product path) */
+#define PD_GEMM_SIMT 1    /* plain fp32 CUDA-core tile kernel: validation arm for the tests  */
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int pd_create(int device_ordinal, pd_handle** out);
+void pd_destroy(pd_handle* h);
+const char* pd_last_error(const pd_handle* h);
+const char* pd_version(void);
+int pd_set_gemm_impl(pd_handle* h, int impl);
+long pd_launch_count(const pd_handle* h); /* kernels enqueued through this handle so far */
+/* 1 (default): kernels that produce tensor-core operands round them to TF32 (rna) so the MMA's
+ * operand truncation is exact; 0: keep full fp32 outputs (used by exactness tests). */
+int pd_set_round_operands(pd_handle* h, int on);
+
+/* ---- dense contraction ------------------------------------------------------------------- */
+/* C[M,N] (=|+=) sum_k A(m,k) * B(n,k)  [+ bias[n]] [+ R[m / r_div, n]] -> act -> (tf32 round)
+ *   a_mn = 0: A stored [M][K] (K contiguous, row stride lda); a_mn = 1: A stored [K][M] (M contiguous).
+ *   b_mn = 0: B stored [N][K] (nn.Linear weight layout);      b_mn = 1: B stored [K][N].
+ *   accumulate = 1: atomically adds into C (split-K over all SMs; bias/R/act must be off).
+ * Replaces every nn.Linear / nn.GRUCell matmul and the conv/deconv contractions:
+ * common.py:47-55, rssm.py:103-116,138-146, rnn.py:60-67, encoders.py:80-90, decoders.py:128-155.
+ * TMA constraints (tcgen05 impl): lda/ldb multiples of 4 elements, base pointers 16-byte aligned. */
+int pd_gemm(pd_handle* h, int M, int N, int K,
+            const float* A, long lda, int a_mn,
+            const float* B, long ldb, int b_mn,
+            float* C, long ldc,
+            const float* bias, const float* R, long ldr, int r_div,
+            int act, int round_out, int accumulate, void* stream);
+
+/* ---- LayerNorm(eps, biased var, affine) + ELU -------------------------------------------- */
+/* y = ELU(LN(x)); saves per-row mean / rstd.  common.py:45-51, rssm.py:105,110,115,139-140,144-145. */
+int pd_ln_elu_fwd(pd_handle* h, int M, int N, const float* x, long ldx,
+                  const float* gamma, const float* beta, float eps,
+                  float* y, long ldy, float* mean, float* rstd, void* stream);
+/* dx from dy; ACCUMULATES dgamma, dbeta and (optional) dbias (= column sums of dx, the grad of the
+ * bias of the Linear that produced x) with atomics. */
+int pd_ln_elu_bwd(pd_handle* h, int M, int N, const float* dy, long lddy,
+                  const float* x, long ldx, const float* y, long ldy,
+                  const float* gamma, const float* mean, const float* rstd,
+                  float* dx, long lddx, float* dgamma, float* dbeta, float* dbias, void* stream);
+
+/* ---- GRU cell pointwise (torch.nn.GRUCell gate order r|u|n) -------------------------------- */
+/* rnn.py:48-49,60-67 -> nn.GRUCell: r=s(gi_r+gh_r) u=s(gi_u+gh_u) n=tanh(gi_n+r*gh_n) h'=(1-u)n+u*h.
+ * gates[M,4,D] (optional) saves r,u,n,gh_n.  hmask (optional): also writes h' * mask_next[m] (the next step's
+ * reset-masked input, rssm.py:134). */
+int pd_gru_fwd(pd_handle* h, int M, int D, const float* gi, long ldgi, const float* gh, long ldgh,
+               const float* hprev, long ldh, float* hout, long ldho,
+               float* hmask, long ldhm, const float* mask_next,
+               float* gates, void* stream);
+/* dh_out = dh_a + dh_b * mask_b (either optional);  outputs dgi[M,3D], dgh[M,3D] and dh_carry = dh_out*u. */
+int pd_gru_bwd(pd_handle* h, int M, int D, const float* dh_a, long ldda, const float* dh_b, long lddb,
+               const float* mask_b, const float* gates, const float* hprev, long ldh,
+               float* dgi, long lddgi, float* dgh, long lddgh, float* dh_carry, long lddc,
+               void* stream);
+
+/* ---- categorical straight-through latent -------------------------------------------------- */
+/* logits[M, G*C] -> per (m,g): l = logits - logsumexp; p = softmax(l); k = argmax_c p_c / q_c
+ * (== torch.multinomial's sampling); z = onehot(k).  C <= 32.
+ * rssm.py:147-148,178-179,195-201; a2c.py:47-48 with G = 1 for the one-hot actor.
+ * zmask (optional) = z * mask_next[m]; idx (optional) int32 [M,G]. */
+int pd_cat_sample(pd_handle* h, int M, int G, int C, const float* logits, long ldl,
+                  const float* noise, long ldn, float* z, long ldz,
+                  float* zmask, long ldzm, const float* mask_next, int32_t* idx, void* stream);
+/* straight-through backward: dlogits = p * (dz - sum_c p dz) + alpha * rowscale[m] * extra;
+ * dz = dz_a + dz_b * mask_b (each optional). */
+int pd_cat_st_bwd(pd_handle* h, int M, int G, int C, const float* logits, long ldl,
+                  const float* dz_a, long ldda, const float* dz_b, long lddb, const float* mask_b,
+                  const float* extra, long ldex, const float* rowscale, float alpha,
+                  float* dlogits, long lddl, void* stream);
+
+/* ---- KL(post || prior) with balancing, entropies, unweighted grads ------------------------ */
+/* dreamer.py:328-343,369-379.  mode 0 (I == 1): value KL, grads (1-bal)*dKL/dpost and bal*dKL/dprior
+ * (bal < 0 => plain KL, kl_balance == 0.5 case dreamer.py:241).  mode 1 (I > 1): sampled
+ * log q(z) - log p(z) with idx from pd_cat_sample.  kl_exact / entropies are for metrics. */
+int pd_kl(pd_handle* h, int M, int G, int C, const float* post, long ldpo, const float* prior, long ldpr,
+          const int32_t* idx, int mode, float balance,
+          float* loss_kl, float* kl_exact, float* ent_post, float* ent_prior,
+          float* dpost, long lddpo, float* dprior, long lddpr, void* stream);
+
+/* ---- convolution data movement (k x k, stride 2, no padding) ------------------------------ */
+/* col[(n,oy,ox), kidx] = in[n, 2oy+kh, 2ox+kw, c]; korder 0: kidx=(kh,kw,c); 1: kidx=(c,kh,kw).
+ * Input addressed by element strides (sN,sY,sX,sC) so NCHW and NHWC both work.
+ * Forward operand of Conv2d (encoders.py:80-88) and backward operand of ConvTranspose2d. */
+int pd_im2col(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, int korder,
+              const float* in, long sN, long sY, long sX, long sC,
+              float* col, long ldcol, int round_out, void* stream);
+/* out[n,y,x,c] = act(bias[c] + sum_{kh,kw: (y-kh)%2==0...} col[(n,(y-kh)/2,(x-kw)/2), (kh,kw,c)]).
+ * Forward of ConvTranspose2d (decoders.py:149-155) and input-gradient of Conv2d. */
+int pd_col2im(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k,
+              const float* col, long ldcol, const float* bias, int act, int round_out,
+              float* out, long sN, long sY, long sX, long sC, void* stream);
+/* Last decoder layer fused with the image loss (decoders.py:163-167): dec NCHW, target NCHW of
+ * image row n / tgt_div; loss[n] = 0.5*sum diff^2; diff stored NHWC for the backward gather. */
+int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k,
+                      const float* col, long ldcol, const float* bias,
+                      const float* target, int tgt_div,
+                      float* dec, float* diff, float* loss, float* csum /* [NB,Cc] per-image channel sums of diff */,
+                      void* stream);
+/* dy <- dy * act'(y) in place (act from output y), db[c] += column sums of the result. */
+int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const float* y, long ldy,
+                    int act, float* db, void* stream);
+/* generic 4-D permutation copy out[perm(i)] (+)= in[i];  dims (HOST int[4]) of `in`, perm[j] (HOST) = source axis of out axis j. */
+int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, const int* perm,
+                int accumulate, int round_out, void* stream);
+
+/* ---- small pointwise / reductions ---------------------------------------------------------- */
+int pd_round_copy(pd_handle* h, const float* src, float* dst, long n, int round_out, void* stream);
+int pd_pad_cols(pd_handle* h, long M, int C, int Cp, const float* src, long lds, float* dst, long ldd, void* stream);
+int pd_mask_rows(pd_handle* h, int M, int N, const float* x, long ldx, const float* mask,
+                 float* out, long ldo, void* stream);
+/* x[m,:] *= alpha * scale[m / scale_div] */
+int pd_rowscale(pd_handle* h, long M, long N, float* x, long ldx, const float* scale, int scale_div, float alpha, void* stream);
+/* out[r, :] = sum_{i<I} x[r*I + i, :]  (undo the IWAE row expansion, rssm.py:35-41) */
+int pd_group_sum(pd_handle* h, long R, int I, int W, const float* x, long ldx, float* out, long ldo, void* stream);
+int pd_colsum(pd_handle* h, long M, int N, const float* x, long ldx, float* out, void* stream); /* out += */
+int pd_fill(pd_handle* h, float* x, long n, float v, void* stream);
+/* reset (uint8/bool [T,B]) -> mask f32 [T, B*I] = !reset   (rssm.py:41) */
+int pd_reset_mask(pd_handle* h, int T, int B, int I, const uint8_t* reset, float* mask, void* stream);
+
+/* ---- scalar-head losses (decoders.py:257-319) ---------------------------------------------- */
+/* kind 0: DenseNormalDecoder  loss = 0.5 (t-y)^2, dy = (y-t);  kind 1: DenseBernoulliDecoder
+ * loss = softplus(y) - t*y, dy = sigmoid(y)-t, rec = sigmoid(y).  target row = m / tgt_div. */
+int pd_scalar_head_loss(pd_handle* h, long M, int kind, const float* y, const float* target, int tgt_div,
+                        float* loss, float* dy, float* rec, void* stream);
+
+/* World-model loss assembly (dreamer.py:362-379, decoders.py:50-108): per (t,b) over I samples.
+ * in: per-row losses [TB*I]; out: w[TB*I] = softmax_i(-L)/(TB) (grad of loss_model wrt L_tbi),
+ * tb[TB,8] = {loss_model, loss_image, loss_reward, loss_terminal, loss_kl(exact), ent_prior, ent_post, 0}. */
+int pd_wm_loss(pd_handle* h, int TB, int I, float kl_weight, float w_img, float w_rew, float w_term,
+               const float* l_img, const float* l_rew, const float* l_term, const float* l_kl,
+               const float* kl_exact, const float* ent_prior, const float* ent_post,
+               float* w, float* tb, void* stream);
+/* out[c] = mean over rows of x[M,N]  (N <= 32) */
+int pd_colmean(pd_handle* h, long M, int N, const float* x, float* out, void* stream);
+
+/* ---- actor-critic (a2c.py:61-149) ---------------------------------------------------------- */
+/* Column-wise GAE(lambda) scan + reality weights + critic loss/grad.  J = H+1 rows of Md columns.
+ * vt = critic_target values, v = critic values, rew = reward head output, term_logit = terminal logits.
+ * outputs: adv, agae, target, weight [H,Md]; dv [H,Md] = d loss_critic / d v; term [J,Md] = sigmoid;
+ * sums[5] (double) += {loss_critic*HMd, sum v0[0], sum v0, sum r1, sum r1^2}. */
+int pd_gae_critic(pd_handle* h, int H, int Md, float gamma, float lambda,
+                  const float* vt, const float* v, const float* rew, const float* term_logit,
+                  float* term, float* adv, float* agae, float* target, float* weight, float* dv,
+                  double* sums, void* stream);
+/* reinforce actor loss, one-hot policy (a2c.py:119-130): rows = H*Md.
+ * sums[2] (double) += {sum (loss_policy - eta*ent)*w, sum ent};  dlogits = d mean(.)/d logits. */
+int pd_actor_loss_onehot(pd_handle* h, long rows, int A, float eta, const float* logits, long ldl,
+                         const float* actions, long lda, const float* agae, const float* weight,
+                         float* dlogits, long lddl, double* sums, void* stream);
+/* tanh_normal policy (functions.py:69-78): out[rows,2A] = (mean_, std_) raw, action in (-1,1). */
+int pd_actor_loss_tanh_normal(pd_handle* h, long rows, int A, float eta, const float* out, long ldo,
+                              const float* actions, long lda, const float* agae, const float* weight,
+                              float* dout, long lddo, double* sums, void* stream);
+/* a = tanh(5 tanh(m/5) + (softplus(s)+0.1) * eps)   (dreamer.py:197-200 with tanh_normal) */
+int pd_tanh_normal_sample(pd_handle* h, long rows, int A, const float* out, long ldo,
+                          const float* eps, float* action, long lda, void* stream);
+
+/* ---- optimizer (dreamer.py:60-87, train.py:193-198) ---------------------------------------- */
+int pd_sumsq(pd_handle* h, const float* x, long n, float* out /* += */, void* stream);
+/* norm = sqrt(*sumsq); coef = min(1, max_norm/(norm+1e-6)); x *= coef; *norm_out = norm
+ * (== torch.nn.utils.clip_grad_norm_). */
+int pd_clip_scale(pd_handle* h, float* x, long n, const float* sumsq, float max_norm, float* norm_out, void* stream);
+/* torch.optim.AdamW (decoupled wd, no amsgrad); *step is a device int32 already incremented. */
+int pd_adamw(pd_handle* h, float* p, const float* g, float* m, float* v, long n,
+             float lr, float beta1, float beta2, float eps, float wd, const int32_t* step, void* stream);
+int pd_inc(pd_handle* h, int32_t* counter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PD_B200_H */

@@ -1,0 +1,77 @@
+// pd_api.cu — handle lifetime, error reporting and the pd_gemm dispatcher of libpd_b200.so.
+#include "pd_common.cuh"
+#include <stdlib.h>
+
+int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
+                           long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream);
+int pd_gemm_simt_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
+                        long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream);
+
+extern "C" {
+
+const char* pd_version(void) { return "pd_b200 0.1 (sm_100a; tcgen05 tf32 + TMA)"; }
+
+int pd_create(int device_ordinal, pd_handle** out) {
+    if (!out) return PD_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ordinal < 0 || device_ordinal >= ndev) return PD_ERR_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return PD_ERR_DEVICE;
+    if (prop.major != 10) return PD_ERR_UNSUPPORTED;   // sm_100a only: no fallback paths
+    pd_handle* h = (pd_handle*)calloc(1, sizeof(pd_handle));
+    if (!h) return PD_ERR_DEVICE;
+    h->device = device_ordinal;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->gemm_impl = PD_GEMM_TCGEN05;
+    h->round_ops = 1;
+    cudaSetDevice(device_ordinal);
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        free(h);
+        return PD_ERR_DEVICE;
+    }
+    h->encode_tiled = fn;
+    *out = h;
+    return PD_OK;
+}
+
+void pd_destroy(pd_handle* h) { free(h); }
+const char* pd_last_error(const pd_handle* h) { return h ? h->err : "null handle"; }
+long pd_launch_count(const pd_handle* h) { return h ? h->launches : 0; }
+
+int pd_set_gemm_impl(pd_handle* h, int impl) {
+    if (!h) return PD_ERR_ARG;
+    PD_REQUIRE(h, impl == PD_GEMM_TCGEN05 || impl == PD_GEMM_SIMT, "unknown gemm impl %d", impl);
+    h->gemm_impl = impl;
+    return PD_OK;
+}
+
+int pd_set_round_operands(pd_handle* h, int on) {
+    if (!h) return PD_ERR_ARG;
+    h->round_ops = on ? 1 : 0;
+    return PD_OK;
+}
+
+int pd_gemm(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn,
+            float* C, long ldc, const float* bias, const float* R, long ldr, int r_div, int act, int round_out,
+            int accumulate, void* stream) {
+    if (!h) return PD_ERR_ARG;
+    PD_REQUIRE(h, M > 0 && N > 0 && K > 0, "pd_gemm: bad shape %d %d %d", M, N, K);
+    PD_REQUIRE(h, A && B && C, "pd_gemm: null operand");
+    PD_REQUIRE(h, !(accumulate && (bias || R || act)), "pd_gemm: accumulate excludes bias/residual/act");
+    PdEpilogue e;
+    e.C = C; e.ldc = ldc; e.bias = bias; e.R = R; e.ldr = ldr; e.r_div = r_div > 0 ? r_div : 1;
+    e.act = act; e.round_out = round_out; e.accumulate = accumulate;
+    // Skinny / unaligned contractions (scalar heads N=1, action inputs K=18, ...) cannot be described
+    // by a TMA tensor map (16-byte strides) and have no tensor-core work to speak of: CUDA cores.
+    const bool tma_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) &&
+                        ((((uintptr_t)B) & 15) == 0) && N >= 8 && K >= 8;
+    if (h->gemm_impl == PD_GEMM_SIMT || !tma_ok)
+        return pd_gemm_simt_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream);
+    return pd_gemm_tcgen05_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// pydreamer_b200 — shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/pd_b200.h"
+
+// ---------------------------------------------------------------------------
+// Handle: host-side state only (no device allocations, see include/pd_b200.h)
+// ---------------------------------------------------------------------------
+struct pd_handle {
+    int device;
+    int num_sms;
+    int gemm_impl;            // PD_GEMM_TCGEN05 / PD_GEMM_SIMT
+    int max_smem_optin;
+    long launches;            // kernels launched through this handle
+    char err[512];
+    void* encode_tiled;       // cuTensorMapEncodeTiled entry point
+    int gemm_smem_configured;
+    int round_ops;            // round tensor-core operands to tf32 (rna) where they are produced
+};
+
+#define PD_FAIL(h, code, ...)                                        \
+    do {                                                             \
+        if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__);    \
+        return (code);                                               \
+    } while (0)
+
+#define PD_CHECK_LAUNCH(h, name)                                                  \
+    do {                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                     \
+        if (e__ != cudaSuccess)                                                   \
+            PD_FAIL(h, PD_ERR_LAUNCH, "%s: %s", name, cudaGetErrorString(e__));   \
+        (h)->launches++;                                                          \
+    } while (0)
+
+#define PD_REQUIRE(h, cond, ...)                                     \
+    do {                                                             \
+        if (!(cond)) PD_FAIL(h, PD_ERR_ARG, __VA_ARGS__);            \
+    } while (0)
+
+static inline int pd_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// Device math helpers
+// ---------------------------------------------------------------------------
+// Round-to-nearest(-away) to TF32 precision (10 explicit mantissa bits).  Producers of
+// tensor-core operands apply this so the hardware's operand truncation is exact
+// (no systematic shrink of every product) — see DESIGN.md "precision".
+__device__ __forceinline__ float pd_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float pd_round_if(float x, int on) { return on ? pd_tf32(x) : x; }
+
+__device__ __forceinline__ float pd_elu(float x) { return x > 0.f ? x : expm1f(x); }
+// d ELU / dx expressed through the ELU *output* y (alpha = 1): x>0 -> 1, else exp(x) = y + 1
+__device__ __forceinline__ float pd_elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+__device__ __forceinline__ float pd_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float pd_softplus(float x) {
+    // torch.nn.functional.softplus(beta=1, threshold=20)
+    return x > 20.f ? x : log1pf(expf(x));
+}
+
+__device__ __forceinline__ float pd_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float pd_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (result valid in all threads).
+__device__ __forceinline__ float pd_block_sum(float v, float* sh /* >= 33 floats */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = pd_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+    if (w == 0) {
+        r = pd_warp_sum(r);
+        if (lane == 0) sh[32] = r;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// ---------------------------------------------------------------------------
+// GEMM epilogue shared by the tcgen05 and the SIMT kernels
+// ---------------------------------------------------------------------------
+struct PdEpilogue {
+    float* C;
+    long ldc;
+    const float* bias;   // [N] or nullptr
+    const float* R;      // residual, row (m / r_div), or nullptr
+    long ldr;
+    int r_div;
+    int act;             // PD_ACT_NONE / PD_ACT_ELU
+    int round_out;       // round result to tf32 precision
+    int accumulate;      // 0: C = v ; 1: atomicAdd(C, v) (split-K safe, no bias/act)
+};
+
+__device__ __forceinline__ float pd_epi_value(const PdEpilogue& e, int row, int col, float acc) {
+    float v = acc;
+    if (e.bias) v += __ldg(e.bias + col);
+    if (e.R) v += __ldg(e.R + (long)(row / e.r_div) * e.ldr + col);
+    if (e.act == PD_ACT_ELU) v = pd_elu(v);
+    if (e.round_out) v = pd_tf32(v);
+    return v;
+}

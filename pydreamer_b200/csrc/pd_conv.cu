@@ -1,0 +1,207 @@
+// pd_conv.cu — data movement for the stride-2 conv encoder / transposed-conv decoder
+// (encoders.py:72-96, decoders.py:111-180).  The contractions themselves run on pd_gemm;
+// these kernels build its operands (im2col) and fold its outputs (col2im), with bias, ELU,
+// the image MSE loss and layout permutes fused in.  All HBM-bound: thread <-> one output
+// element with the channel index fastest so that global accesses coalesce.
+#include "pd_common.cuh"
+
+namespace {
+
+__global__ void im2col_kernel(long total, int Hout, int Wout, int Cc, int k, int korder,
+                              const float* __restrict__ in, long sN, long sY, long sX, long sC,
+                              float* __restrict__ col, long ldcol, int round_out) {
+    const int KK = k * k * Cc;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long row = idx / KK;
+        int kidx = (int)(idx % KK);
+        int ox = (int)(row % Wout);
+        long t = row / Wout;
+        int oy = (int)(t % Hout);
+        long n = t / Hout;
+        int c, kh, kw;
+        if (korder == 0) { c = kidx % Cc; int r = kidx / Cc; kw = r % k; kh = r / k; }
+        else             { kw = kidx % k; int r = kidx / k; kh = r % k; c = r / k; }
+        float v = in[n * sN + (long)(2 * oy + kh) * sY + (long)(2 * ox + kw) * sX + (long)c * sC];
+        col[row * ldcol + kidx] = pd_round_if(v, round_out);
+    }
+}
+
+__device__ __forceinline__ float col2im_gather(const float* __restrict__ col, long ldcol, long n, int y, int x, int c,
+                                               int Hin, int Win, int Cc, int k) {
+    float acc = 0.f;
+    for (int kh = y & 1; kh < k; kh += 2) {
+        int iy = (y - kh) >> 1;
+        if (iy < 0) break;
+        if (iy >= Hin) continue;
+        for (int kw = x & 1; kw < k; kw += 2) {
+            int ix = (x - kw) >> 1;
+            if (ix < 0) break;
+            if (ix >= Win) continue;
+            acc += col[((n * Hin + iy) * Win + ix) * ldcol + (long)(kh * k + kw) * Cc + c];
+        }
+    }
+    return acc;
+}
+
+__global__ void col2im_kernel(long total, int Hin, int Win, int Hout, int Wout, int Cc, int k,
+                              const float* __restrict__ col, long ldcol, const float* __restrict__ bias, int act,
+                              int round_out, float* __restrict__ out, long sN, long sY, long sX, long sC) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % Cc);
+        long t = idx / Cc;
+        int x = (int)(t % Wout);
+        t /= Wout;
+        int y = (int)(t % Hout);
+        long n = t / Hout;
+        float v = col2im_gather(col, ldcol, n, y, x, c, Hin, Win, Cc, k);
+        if (bias) v += bias[c];
+        if (act == PD_ACT_ELU) v = pd_elu(v);
+        out[n * sN + (long)y * sY + (long)x * sX + (long)c * sC] = pd_round_if(v, round_out);
+    }
+}
+
+// One block per decoded image: NCHW traversal (x fastest) for coalesced dec/target/diff access.
+__global__ void __launch_bounds__(256)
+col2im_imgloss_kernel(int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* __restrict__ col, long ldcol,
+                      const float* __restrict__ bias, const float* __restrict__ target, int tgt_div,
+                      float* __restrict__ dec, float* __restrict__ diff, float* __restrict__ loss,
+                      float* __restrict__ csum) {
+    __shared__ float sh[33];
+    const long n = blockIdx.x;
+    const int plane = Hout * Wout;
+    const int per = Cc * plane;
+    const float* tg = target + (n / tgt_div) * (long)per;
+    float acc = 0.f;
+    for (int c = 0; c < Cc; ++c) {
+        float cacc = 0.f;
+        for (int i = threadIdx.x; i < plane; i += blockDim.x) {
+            int x = i % Wout;
+            int y = i / Wout;
+            float v = col2im_gather(col, ldcol, n, y, x, c, Hin, Win, Cc, k) + bias[c];
+            float d = v - tg[c * plane + i];
+            dec[n * per + c * plane + i] = v;
+            diff[n * per + c * plane + i] = d;
+            acc += d * d;
+            cacc += d;
+        }
+        float cs = pd_block_sum(cacc, sh);
+        if (threadIdx.x == 0) csum[n * Cc + c] = cs;
+    }
+    float s = pd_block_sum(acc, sh);
+    if (threadIdx.x == 0) loss[n] = 0.5f * s;
+}
+
+// dy <- dy * act'(y);  db[c] += sum_rows.  blockDim = (32, 8): a warp owns 32 consecutive columns.
+__global__ void bias_act_bwd_kernel(long M, int N, float* __restrict__ dy, long lddy, const float* __restrict__ y,
+                                    long ldy, int act, float* db, int round_out) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (c < N) {
+        for (long r = (long)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += (long)gridDim.y * blockDim.y) {
+            float g = dy[r * lddy + c];
+            if (act == PD_ACT_ELU) {
+                g *= pd_elu_grad_from_out(y[r * ldy + c]);
+                dy[r * lddy + c] = pd_round_if(g, round_out);
+            }
+            acc += g;
+        }
+    }
+    __shared__ float sh[8][33];
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N && db) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
+        atomicAdd(db + c, s);
+    }
+}
+
+struct Perm4 { int d[4]; long so[4]; };   // d: dims of `in`; so[a]: stride in `out` of in-axis a
+
+__global__ void permute4_kernel(long total, Perm4 p, const float* __restrict__ in, float* __restrict__ out,
+                                int accumulate, int round_out) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long t = idx;
+        int i3 = (int)(t % p.d[3]); t /= p.d[3];
+        int i2 = (int)(t % p.d[2]); t /= p.d[2];
+        int i1 = (int)(t % p.d[1]); t /= p.d[1];
+        int i0 = (int)t;
+        long o = i0 * p.so[0] + i1 * p.so[1] + i2 * p.so[2] + i3 * p.so[3];
+        float v = in[idx];
+        if (accumulate) out[o] += v;
+        else out[o] = pd_round_if(v, round_out);
+    }
+}
+
+inline int grid_for(long total, int block, int num_sms) {
+    long g = (total + block - 1) / block;
+    long cap = (long)num_sms * 32;
+    return (int)(g < cap ? g : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pd_im2col(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, int korder, const float* in, long sN, long sY,
+              long sX, long sC, float* col, long ldcol, int round_out, void* stream) {
+    PD_REQUIRE(h, Hin >= k && Win >= k, "pd_im2col: input %dx%d smaller than kernel %d", Hin, Win, k);
+    int Hout = (Hin - k) / 2 + 1, Wout = (Win - k) / 2 + 1;
+    long total = (long)NB * Hout * Wout * k * k * Cc;
+    im2col_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        total, Hout, Wout, Cc, k, korder, in, sN, sY, sX, sC, col, ldcol, round_out && h->round_ops);
+    PD_CHECK_LAUNCH(h, "im2col");
+    return PD_OK;
+}
+
+int pd_col2im(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* col, long ldcol,
+              const float* bias, int act, int round_out, float* out, long sN, long sY, long sX, long sC,
+              void* stream) {
+    long total = (long)NB * Hout * Wout * Cc;
+    col2im_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        total, Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, act, round_out && h->round_ops, out, sN, sY, sX, sC);
+    PD_CHECK_LAUNCH(h, "col2im");
+    return PD_OK;
+}
+
+int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, const float* col, long ldcol,
+                      const float* bias, const float* target, int tgt_div, float* dec, float* diff, float* loss,
+                      float* csum, void* stream) {
+    int Hout = (Hin - 1) * 2 + k, Wout = (Win - 1) * 2 + k;
+    col2im_imgloss_kernel<<<NB, 256, 0, (cudaStream_t)stream>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target,
+                                                                tgt_div > 0 ? tgt_div : 1, dec, diff, loss, csum);
+    PD_CHECK_LAUNCH(h, "col2im_imgloss");
+    return PD_OK;
+}
+
+int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const float* y, long ldy, int act, float* db,
+                    void* stream) {
+    dim3 block(32, 8);
+    long gy = (M + 63) / 64;
+    long cap = (long)h->num_sms * 8 / ((N + 31) / 32);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    dim3 grid((N + 31) / 32, (unsigned)gy);
+    bias_act_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(M, N, dy, lddy, y, ldy, act, db, h->round_ops);
+    PD_CHECK_LAUNCH(h, "bias_act_bwd");
+    return PD_OK;
+}
+
+int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, const int* perm, int accumulate,
+                int round_out, void* stream) {
+    // out axis j takes in axis perm[j]; out is contiguous in its own (permuted) shape.
+    Perm4 p;
+    long ostride[4];
+    long s = 1;
+    for (int j = 3; j >= 0; --j) { ostride[j] = s; s *= dims[perm[j]]; }
+    for (int a = 0; a < 4; ++a) p.d[a] = dims[a];
+    for (int j = 0; j < 4; ++j) p.so[perm[j]] = ostride[j];
+    long total = (long)dims[0] * dims[1] * dims[2] * dims[3];
+    permute4_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(total, p, in, out, accumulate,
+                                                                                      round_out && h->round_ops);
+    PD_CHECK_LAUNCH(h, "permute4");
+    return PD_OK;
+}
+
+}  // extern "C"

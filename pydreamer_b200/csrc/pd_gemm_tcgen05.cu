@@ -1,0 +1,346 @@
+// pd_gemm_tcgen05.cu — persistent, warp-specialised TF32 GEMM for sm_100a.
+//
+//   C[M,N] (=|+=) sum_k A(m,k) * B(n,k) (+bias)(+residual) -> act
+//
+// Pipeline (one CTA per SM, 192 threads):
+//   warp 0      : TMA producer  — cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) into a 6-stage smem ring
+//   warp 1      : MMA issuer    — one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (128x128x8)
+//                                 with the fp32 accumulator tile in TMEM (double buffered, 2 x 128 columns)
+//   warps 2..5  : epilogue      — tcgen05.ld 32x32b.x32 -> registers -> bias/residual/ELU -> global
+// Work units are (m-tile, n-tile, k-split); split-K units add into C with red.global.add.f32.
+//
+// Operand layouts: both operands may be K-major ([rows][K], K contiguous) or MN-major ([K][rows]);
+// the second form lets the backward contractions dX = dY*W and dW = dY^T*X read the forward tensors
+// in place (no transposes in HBM).  Smem tiles follow the canonical UMMA layouts
+// (K-major:  8-row x 128 B swizzle atoms, SBO = 1024 B;
+//  MN-major: 32-element x 8-k atoms,      LBO = 4096 B between 32-wide MN groups, SBO = 1024 B).
+#include "pd_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;           // UMMA M
+constexpr int BN = 128;           // UMMA N
+constexpr int BK = 32;            // fp32 elements per k-block = 128 B = one swizzle row
+constexpr int UMMA_K = 8;         // tf32: 32 B per instruction
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int B_BYTES = BN * BK * 4;   // 16 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;   // 256 (power of two)
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+    int M, N, K;
+    int a_mn, b_mn;
+    int num_m, num_n, splits, kb_total, kb_per_split;
+    PdEpilogue epi;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();   // watchdog: a broken pipeline must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + STAGES;             // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;         // [ACC_STAGES]
+    uint64_t* tempty = bars + 2 * STAGES + ACC_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int units = g.num_m * g.num_n * g.splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int split = u % g.splits;
+                const int tile = u / g.splits;
+                const int m0 = (tile / g.num_n) * BM;
+                const int n0 = (tile % g.num_n) * BN;
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    if (!g.a_mn) {
+                        tma_load_2d(&tmA, &full[stage], sa, k0, m0);              // box {32 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j)                        // box {32 m, 32 k} x 4
+                            tma_load_2d(&tmA, &full[stage], sa + j * 4096, m0 + j * 32, k0);
+                    }
+                    if (!g.b_mn) {
+                        tma_load_2d(&tmB, &full[stage], sb, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_2d(&tmB, &full[stage], sb + j * 4096, n0 + j * 32, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor (cute InstrDescriptor): c=F32, a=b=TF32, majors, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) |
+                                   ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int split = u % g.splits;
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int s = 0; s < BK / UMMA_K; ++s) {
+                        const uint64_t ad = g.a_mn ? make_desc(sa + s * 1024, 4096, 1024)
+                                                   : make_desc(sa + s * 32, 16, 1024);
+                        const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, 4096, 1024)
+                                                   : make_desc(sb + s * 32, 16, 1024);
+                        tc_mma_tf32(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[as]);                 // accumulator tile complete
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        int as = 0; uint32_t aphase = 0;
+        const PdEpilogue& e = g.epi;
+        const bool vec_ok = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int tile = u / g.splits;
+            const int m0 = (tile / g.num_n) * BM;
+            const int n0 = (tile % g.num_n) * BN;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);     // warp-collective: no divergence above
+                const int col0 = n0 + c * 32;
+                if (row < g.M && col0 < g.N) {
+                    float* crow = e.C + (long)row * e.ldc;
+                    if (e.accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < g.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 32; j4 += 4) {
+                            const int col = col0 + j4;
+                            if (vec_ok && col + 3 < g.N) {
+                                float4 v;
+                                v.x = pd_epi_value(e, row, col + 0, __uint_as_float(r[j4 + 0]));
+                                v.y = pd_epi_value(e, row, col + 1, __uint_as_float(r[j4 + 1]));
+                                v.z = pd_epi_value(e, row, col + 2, __uint_as_float(r[j4 + 2]));
+                                v.w = pd_epi_value(e, row, col + 3, __uint_as_float(r[j4 + 3]));
+                                *reinterpret_cast<float4*>(crow + col) = v;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (col + j < g.N)
+                                        crow[col + j] = pd_epi_value(e, row, col + j, __uint_as_float(r[j4 + j]));
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp32 tensor map: dim0 = contiguous dimension.
+int make_map(pd_handle* h, CUtensorMap* tm, const float* base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems,
+             uint32_t box0, uint32_t box1) {
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstride[1] = {ld_elems * 4};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride,
+                                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu", (int)r,
+                                   (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)ld_elems);
+    return PD_OK;
+}
+
+}  // namespace
+
+int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
+                           long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream) {
+    PD_REQUIRE(h, (lda % 4) == 0 && (ldb % 4) == 0, "pd_gemm(tcgen05): lda/ldb must be multiples of 4 (got %ld, %ld)",
+               lda, ldb);
+    PD_REQUIRE(h, (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "pd_gemm(tcgen05): A/B must be 16B aligned");
+    if (!h->gemm_smem_configured) {
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
+        h->gemm_smem_configured = 1;
+    }
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+    else       rc = make_map(h, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BK);
+    if (rc) return rc;
+    if (!b_mn) rc = make_map(h, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+    else       rc = make_map(h, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BK);
+    if (rc) return rc;
+
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.a_mn = a_mn; g.b_mn = b_mn;
+    g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
+    g.kb_total = pd_cdiv(K, BK);
+    g.epi = epi;
+    int tiles = g.num_m * g.num_n;
+    int splits = 1;
+    if (epi.accumulate && tiles < h->num_sms) {
+        // split-K: spread the contraction over idle SMs, keep >= 8 k-blocks per unit
+        splits = h->num_sms / tiles;
+        int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    g.kb_per_split = pd_cdiv(g.kb_total, splits);
+    g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units
+    int units = tiles * g.splits;
+    int grid = units < h->num_sms ? units : h->num_sms;
+    pd_gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, g);
+    PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel");
+    return PD_OK;
+}

@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI (include/pd_b200.h).
+
+`NativeOps` is the product path: every method enqueues one hand-written sm_100a kernel on the
+current CUDA stream through libpd_b200.so.  There is no CPU implementation in this package: the
+constructor raises if CUDA or the library is unavailable.
+
+Tests may install a reference implementation of the *same interface* (oracle/ref_ops.py, plain
+torch) with `set_ops_for_testing` to check the host-side composition and hand-written backward of
+pydreamer_b200.dreamer on CPU; that hook is refused unless PD_B200_TESTING=1 is set by the test
+harness, so a product run can never route through it.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _native
+
+ACT_NONE, ACT_ELU = 0, 1
+GEMM_TCGEN05, GEMM_SIMT = 0, 1
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _ld(t):
+    """Row stride (elements) of a 2-D view whose last dim is contiguous."""
+    assert t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1), (t.shape, t.stride())
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+class NativeOps:
+    is_reference = False
+
+    def __init__(self, device):
+        device = torch.device(device)
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("pydreamer_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+        self.device = device
+        self.lib = _native.load()
+        h = ctypes.c_void_p()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        rc = self.lib.pd_create(int(idx), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"pd_create failed ({rc}): device {idx} is not an sm_100 GPU or the driver is too old")
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.pd_destroy(self.h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _s(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc, name):
+        if rc != 0:
+            raise RuntimeError(f"{name} failed ({rc}): {self.lib.pd_last_error(self.h).decode()}")
+
+    def set_gemm_impl(self, impl):
+        self._ck(self.lib.pd_set_gemm_impl(self.h, int(impl)), "pd_set_gemm_impl")
+
+    def set_round_operands(self, on):
+        self._ck(self.lib.pd_set_round_operands(self.h, int(bool(on))), "pd_set_round_operands")
+
+    def launch_count(self):
+        return int(self.lib.pd_launch_count(self.h))
+
+    # ------------------------------------------------------------------ gemm
+    def gemm(self, A, B, C, *, a_mn=False, b_mn=False, bias=None, res=None, r_div=1, act=ACT_NONE,
+             round_out=False, accumulate=False):
+        """C[M,N] (=|+=) A(m,k) B(n,k).  A: [M,K] (or stored [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn)."""
+        M, N = C.shape
+        K = A.shape[0] if a_mn else A.shape[1]
+        assert (A.shape[1] if a_mn else A.shape[0]) == M, (A.shape, C.shape, a_mn)
+        assert (B.shape == (K, N)) if b_mn else (B.shape == (N, K)), (B.shape, (N, K), b_mn)
+        rc = self.lib.pd_gemm(self.h, M, N, K, _ptr(A), _ld(A), int(a_mn), _ptr(B), _ld(B), int(b_mn),
+                              _ptr(C), _ld(C), _ptr(bias), _ptr(res), _ld(res) if res is not None else 0,
+                              int(r_div), int(act), int(round_out), int(accumulate), self._s())
+        self._ck(rc, "pd_gemm")
+        return C
+
+    # ------------------------------------------------------------------ rowwise
+    def ln_elu_fwd(self, x, gamma, beta, eps, y, mean, rstd):
+        M, N = x.shape
+        self._ck(self.lib.pd_ln_elu_fwd(self.h, M, N, _ptr(x), _ld(x), _ptr(gamma), _ptr(beta), float(eps),
+                                        _ptr(y), _ld(y), _ptr(mean), _ptr(rstd), self._s()), "pd_ln_elu_fwd")
+
+    def ln_elu_bwd(self, dy, x, y, gamma, mean, rstd, dx, dgamma, dbeta, dbias=None):
+        M, N = x.shape
+        self._ck(self.lib.pd_ln_elu_bwd(self.h, M, N, _ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(y), _ld(y),
+                                        _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ld(dx), _ptr(dgamma),
+                                        _ptr(dbeta), _ptr(dbias), self._s()), "pd_ln_elu_bwd")
+
+    def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None):
+        M, D = hprev.shape
+        self._ck(self.lib.pd_gru_fwd(self.h, M, D, _ptr(gi), _ld(gi), _ptr(gh), _ld(gh), _ptr(hprev), _ld(hprev),
+                                     _ptr(hout), _ld(hout), _ptr(hmask), _ld(hmask) if hmask is not None else 0,
+                                     _ptr(mask_next), _ptr(gates), self._s()), "pd_gru_fwd")
+
+    def gru_bwd(self, dh_a, dh_b, mask_b, gates, hprev, dgi, dgh, dh_carry):
+        M, D = hprev.shape
+        self._ck(self.lib.pd_gru_bwd(self.h, M, D, _ptr(dh_a), _ld(dh_a) if dh_a is not None else 0, _ptr(dh_b),
+                                     _ld(dh_b) if dh_b is not None else 0, _ptr(mask_b), _ptr(gates), _ptr(hprev),
+                                     _ld(hprev), _ptr(dgi), _ld(dgi), _ptr(dgh), _ld(dgh), _ptr(dh_carry),
+                                     _ld(dh_carry), self._s()), "pd_gru_bwd")
+
+    def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None):
+        M = logits.shape[0]
+        self._ck(self.lib.pd_cat_sample(self.h, M, G, C, _ptr(logits), _ld(logits), _ptr(noise), _ld(noise), _ptr(z),
+                                        _ld(z), _ptr(zmask), _ld(zmask) if zmask is not None else 0, _ptr(mask_next),
+                                        _ptr(idx), self._s()), "pd_cat_sample")
+
+    def cat_st_bwd(self, logits, G, C, dz_a, dz_b, mask_b, extra, rowscale, alpha, dlogits):
+        M = logits.shape[0]
+        self._ck(self.lib.pd_cat_st_bwd(self.h, M, G, C, _ptr(logits), _ld(logits), _ptr(dz_a),
+                                        _ld(dz_a) if dz_a is not None else 0, _ptr(dz_b),
+                                        _ld(dz_b) if dz_b is not None else 0, _ptr(mask_b), _ptr(extra),
+                                        _ld(extra) if extra is not None else 0, _ptr(rowscale), float(alpha),
+                                        _ptr(dlogits), _ld(dlogits), self._s()), "pd_cat_st_bwd")
+
+    def kl(self, post, prior, idx, mode, balance, G, C, loss_kl, kl_exact, ent_post, ent_prior, dpost, dprior):
+        M = post.shape[0]
+        self._ck(self.lib.pd_kl(self.h, M, G, C, _ptr(post), _ld(post), _ptr(prior), _ld(prior), _ptr(idx), int(mode),
+                                float(balance), _ptr(loss_kl), _ptr(kl_exact), _ptr(ent_post), _ptr(ent_prior),
+                                _ptr(dpost), _ld(dpost), _ptr(dprior), _ld(dprior), self._s()), "pd_kl")
+
+    # ------------------------------------------------------------------ conv data movement
+    def im2col(self, inp, k, korder, col, round_out=True):
+        """inp: 4-D view indexed [n, y, x, c] (any strides); col: [NB*Ho*Wo, k*k*C]."""
+        NB, Hin, Win, Cc = inp.shape
+        sN, sY, sX, sC = inp.stride()
+        self._ck(self.lib.pd_im2col(self.h, NB, Hin, Win, Cc, k, korder, _ptr(inp), sN, sY, sX, sC, _ptr(col),
+                                    _ld(col), int(round_out), self._s()), "pd_im2col")
+
+    def col2im(self, col, Hin, Win, k, bias, act, out, round_out=True):
+        """out: 4-D view indexed [n, y, x, c]; col: [NB*Hin*Win, k*k*C]."""
+        NB, Hout, Wout, Cc = out.shape
+        sN, sY, sX, sC = out.stride()
+        self._ck(self.lib.pd_col2im(self.h, NB, Hin, Win, Hout, Wout, Cc, k, _ptr(col), _ld(col), _ptr(bias), int(act),
+                                    int(round_out), _ptr(out), sN, sY, sX, sC, self._s()), "pd_col2im")
+
+    def col2im_imgloss(self, col, NB, Hin, Win, Cc, k, bias, target, tgt_div, dec, diff, loss, csum):
+        self._ck(self.lib.pd_col2im_imgloss(self.h, NB, Hin, Win, Cc, k, _ptr(col), _ld(col), _ptr(bias), _ptr(target),
+                                            int(tgt_div), _ptr(dec), _ptr(diff), _ptr(loss), _ptr(csum), self._s()),
+                 "pd_col2im_imgloss")
+
+    def bias_act_bwd(self, dy, y, act, db):
+        M, N = dy.shape
+        self._ck(self.lib.pd_bias_act_bwd(self.h, M, N, _ptr(dy), _ld(dy), _ptr(y), _ld(y) if y is not None else 0,
+                                          int(act), _ptr(db), self._s()), "pd_bias_act_bwd")
+
+    def permute4(self, inp, out, perm, accumulate=False, round_out=False):
+        """out (contiguous, shape = inp.shape permuted by perm) (+)= inp.permute(perm)."""
+        assert inp.is_contiguous() and out.is_contiguous() and inp.dim() == 4
+        dims = (ctypes.c_int * 4)(*inp.shape)
+        pm = (ctypes.c_int * 4)(*perm)
+        self._ck(self.lib.pd_permute4(self.h, _ptr(inp), _ptr(out), dims, pm, int(accumulate), int(round_out),
+                                      self._s()), "pd_permute4")
+
+    # ------------------------------------------------------------------ small ops
+    def round_copy(self, src, dst, round_out=True):
+        assert src.is_contiguous() and dst.is_contiguous()
+        self._ck(self.lib.pd_round_copy(self.h, _ptr(src), _ptr(dst), src.numel(), int(round_out), self._s()),
+                 "pd_round_copy")
+
+    def mask_rows(self, x, mask, out):
+        M, N = x.shape
+        self._ck(self.lib.pd_mask_rows(self.h, M, N, _ptr(x), _ld(x), _ptr(mask), _ptr(out), _ld(out), self._s()),
+                 "pd_mask_rows")
+
+    def rowscale(self, x, scale, scale_div=1, alpha=1.0):
+        M, N = x.shape
+        self._ck(self.lib.pd_rowscale(self.h, M, N, _ptr(x), _ld(x), _ptr(scale), int(scale_div), float(alpha),
+                                      self._s()), "pd_rowscale")
+
+    def group_sum(self, x, I, out):
+        R, W = out.shape
+        self._ck(self.lib.pd_group_sum(self.h, R, I, W, _ptr(x), _ld(x), _ptr(out), _ld(out), self._s()),
+                 "pd_group_sum")
+
+    def colsum(self, x, out):
+        M, N = x.shape
+        self._ck(self.lib.pd_colsum(self.h, M, N, _ptr(x), _ld(x), _ptr(out), self._s()), "pd_colsum")
+
+    def fill(self, x, v=0.0):
+        assert x.is_contiguous()
+        self._ck(self.lib.pd_fill(self.h, _ptr(x), x.numel(), float(v), self._s()), "pd_fill")
+
+    def reset_mask(self, reset, I, mask):
+        T, B = reset.shape
+        r = reset.contiguous().view(torch.uint8) if reset.dtype == torch.bool else reset.to(torch.uint8)
+        self._ck(self.lib.pd_reset_mask(self.h, T, B, I, _ptr(r), _ptr(mask), self._s()), "pd_reset_mask")
+
+    def scalar_head_loss(self, kind, y, target, tgt_div, loss, dy, rec):
+        self._ck(self.lib.pd_scalar_head_loss(self.h, y.numel(), int(kind), _ptr(y), _ptr(target), int(tgt_div),
+                                              _ptr(loss), _ptr(dy), _ptr(rec), self._s()), "pd_scalar_head_loss")
+
+    def wm_loss(self, TB, I, kl_weight, w_img, w_rew, w_term, l_img, l_rew, l_term, l_kl, kl_exact, ent_prior,
+                ent_post, w, tb):
+        self._ck(self.lib.pd_wm_loss(self.h, TB, I, float(kl_weight), float(w_img), float(w_rew), float(w_term),
+                                     _ptr(l_img), _ptr(l_rew), _ptr(l_term), _ptr(l_kl), _ptr(kl_exact),
+                                     _ptr(ent_prior), _ptr(ent_post), _ptr(w), _ptr(tb), self._s()), "pd_wm_loss")
+
+    def colmean(self, x, out):
+        M, N = x.shape
+        assert x.is_contiguous()
+        self._ck(self.lib.pd_colmean(self.h, M, N, _ptr(x), _ptr(out), self._s()), "pd_colmean")
+
+    # ------------------------------------------------------------------ actor critic
+    def gae_critic(self, H, Md, gamma, lam, vt, v, rew, term_logit, term, adv, agae, target, weight, dv, sums):
+        self._ck(self.lib.pd_gae_critic(self.h, H, Md, float(gamma), float(lam), _ptr(vt), _ptr(v), _ptr(rew),
+                                        _ptr(term_logit), _ptr(term), _ptr(adv), _ptr(agae), _ptr(target),
+                                        _ptr(weight), _ptr(dv), _ptr(sums), self._s()), "pd_gae_critic")
+
+    def actor_loss_onehot(self, eta, logits, actions, agae, weight, dlogits, sums):
+        rows, A = actions.shape
+        self._ck(self.lib.pd_actor_loss_onehot(self.h, rows, A, float(eta), _ptr(logits), _ld(logits), _ptr(actions),
+                                               _ld(actions), _ptr(agae), _ptr(weight), _ptr(dlogits), _ld(dlogits),
+                                               _ptr(sums), self._s()), "pd_actor_loss_onehot")
+
+    def actor_loss_tanh_normal(self, eta, out, actions, agae, weight, dout, sums):
+        rows, A = actions.shape
+        self._ck(self.lib.pd_actor_loss_tanh_normal(self.h, rows, A, float(eta), _ptr(out), _ld(out), _ptr(actions),
+                                                    _ld(actions), _ptr(agae), _ptr(weight), _ptr(dout), _ld(dout),
+                                                    _ptr(sums), self._s()), "pd_actor_loss_tanh_normal")
+
+    def tanh_normal_sample(self, out, eps, action):
+        rows, A = action.shape
+        self._ck(self.lib.pd_tanh_normal_sample(self.h, rows, A, _ptr(out), _ld(out), _ptr(eps), _ptr(action),
+                                                _ld(action), self._s()), "pd_tanh_normal_sample")
+
+    # ------------------------------------------------------------------ optimizer
+    def sumsq(self, x, out):
+        assert x.is_contiguous()
+        self._ck(self.lib.pd_sumsq(self.h, _ptr(x), x.numel(), _ptr(out), self._s()), "pd_sumsq")
+
+    def clip_scale(self, x, sumsq, max_norm, norm_out):
+        self._ck(self.lib.pd_clip_scale(self.h, _ptr(x), x.numel(), _ptr(sumsq), float(max_norm), _ptr(norm_out),
+                                        self._s()), "pd_clip_scale")
+
+    def adamw(self, p, g, m, v, lr, beta1, beta2, eps, wd, step):
+        self._ck(self.lib.pd_adamw(self.h, _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1),
+                                   float(beta2), float(eps), float(wd), _ptr(step), self._s()), "pd_adamw")
+
+    def inc(self, counter):
+        self._ck(self.lib.pd_inc(self.h, _ptr(counter), self._s()), "pd_inc")
+
+
+# ---------------------------------------------------------------------- ops registry
+_TEST_OPS = None
+
+
+def set_ops_for_testing(ops):
+    """Install a reference op table (tests only; see module docstring)."""
+    global _TEST_OPS
+    if ops is not None and os.environ.get("PD_B200_TESTING") != "1":
+        raise RuntimeError("set_ops_for_testing is only available to the test harness (PD_B200_TESTING=1)")
+    _TEST_OPS = ops
+
+
+def get_ops(device):
+    if _TEST_OPS is not None:
+        return _TEST_OPS
+    return NativeOps(device)

@@ -1,0 +1,386 @@
+"""GPU parity tests: every hand-written kernel (through the C ABI) against oracle/ref_ops.py on the
+same seeded inputs.  Tolerances are written next to each check:
+  * tcgen05 GEMM with integer-valued operands: bit-exact (tf32 holds them exactly, fp32 sums exact)
+  * tcgen05 GEMM with random fp32 operands:   1e-3 of the output scale (TF32 operand precision)
+  * pointwise / rowwise kernels (operand rounding off): 1e-5 relative
+  * categorical sample indices: bit-exact."""
+import pytest
+import torch
+
+from oracle.ref_ops import RefOps
+
+import os
+
+pytestmark = pytest.mark.gpu
+# PD_TEST_DEV=cpu runs this file with the reference table on both sides: a dry run of the test code itself
+DEV = os.environ.get("PD_TEST_DEV", "cuda:0")
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def ints(*shape, seed=0, lo=-4, hi=5):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return torch.randint(lo, hi, shape, generator=g).float().to(DEV)
+
+
+def close(a, b, rtol=1e-5, atol=1e-6, what=""):
+    err = (a.double() - b.double()).abs().max().item()
+    ref = b.double().abs().max().item()
+    assert err <= atol + rtol * max(ref, 1e-30), f"{what}: max err {err:.3e} vs scale {ref:.3e}"
+
+
+@pytest.fixture(scope="module")
+def ops(request):
+    if DEV == "cpu":
+        yield RefOps("cpu")
+        return
+    native_ops = request.getfixturevalue("native_ops")
+    native_ops.set_round_operands(False)
+    yield native_ops
+    native_ops.set_round_operands(True)
+    native_ops.set_gemm_impl(0)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefOps(DEV)
+
+
+GEMM_SHAPES = [(128, 128, 32), (128, 128, 256), (50, 1000, 1024), (300, 6144, 1000), (130, 264, 100), (64, 48, 48),
+               (257, 1000, 2048), (2500, 400, 3072), (900, 108, 48)]
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_exact_on_integer_operands(ops, ref, impl, a_mn, b_mn, M, N, K):
+    ops.set_gemm_impl(impl)
+    A = ints(K, M, seed=1) if a_mn else ints(M, K, seed=1)
+    B = ints(K, N, seed=2) if b_mn else ints(N, K, seed=2)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    Cr = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, C, a_mn=a_mn, b_mn=b_mn)
+    ref.gemm(A, B, Cr, a_mn=a_mn, b_mn=b_mn)
+    assert torch.equal(C, Cr), f"max diff {(C - Cr).abs().max().item()}"
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_gemm_epilogue_bias_residual_elu_and_strided_views(ops, ref, impl):
+    ops.set_gemm_impl(impl)
+    M, N, K, I = 96, 1000, 512, 4
+    big = ints(M, K + 64, seed=3)
+    A = big[:, 32:32 + K]                       # strided view (lda = K+64, offset 128 B)
+    B = ints(N, K, seed=4)
+    bias = ints(N, seed=5)
+    res = ints(M // I, N, seed=6)
+    Cbig = torch.zeros(M, N + 24, device=DEV)
+    C = Cbig[:, 8:8 + N]                        # ldc = N+24, 32 B offset
+    Cr = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, C, bias=bias, res=res, r_div=I, act=1)
+    ref.gemm(A, B, Cr, bias=bias, res=res, r_div=I, act=1)
+    close(C, Cr, rtol=1e-6, what="epilogue")
+    assert Cbig[:, :8].abs().sum() == 0 and Cbig[:, 8 + N:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("M,N,K", [(108, 48, 90000), (1000, 2048, 2500), (400, 400, 40000), (48, 48, 5000)])
+def test_gemm_splitk_accumulate_both_mn_major(ops, ref, impl, M, N, K):
+    """weight-gradient form: C[M,N] += sum_k A[k,m] B[k,n]"""
+    ops.set_gemm_impl(impl)
+    A, B = ints(K, M, seed=7, lo=-2, hi=3), ints(K, N, seed=8, lo=-2, hi=3)
+    C = ints(M, N, seed=9)
+    Cr = C.clone()
+    ops.gemm(A, B, C, a_mn=1, b_mn=1, accumulate=True)
+    ref.gemm(A, B, Cr, a_mn=1, b_mn=1, accumulate=True)
+    assert torch.equal(C, Cr), f"max diff {(C - Cr).abs().max().item()}"
+
+
+def test_gemm_tf32_error_on_random_operands(ops, native_ops):
+    if DEV == "cpu":
+        pytest.skip("dry run")
+    ops.set_gemm_impl(0)
+    M, N, K = 512, 1024, 2048
+    A, B = rnd(M, K, seed=10), rnd(N, K, scale=0.05, seed=11)
+    C = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, C)
+    exact = A.double() @ B.double().t()
+    err = (C.double() - exact).abs().max().item() / exact.abs().max().item()
+    bias = ((C.double() - exact) * exact.sign()).mean().item() / exact.abs().mean().item()
+    print(f"tf32 gemm (raw fp32 operands): max rel err {err:.3e}, signed mean shrink {bias:.3e}")
+    assert err < 2e-3
+    # operands pre-rounded to tf32 (what the producers do): error drops to accumulation order only
+    At = torch.empty_like(A); Bt = torch.empty_like(B)
+    native_ops.set_round_operands(True)
+    ops.round_copy(A, At); ops.round_copy(B, Bt)
+    native_ops.set_round_operands(False)
+    ops.gemm(At, Bt, C)
+    exact_t = At.double() @ Bt.double().t()
+    err_t = (C.double() - exact_t).abs().max().item() / exact_t.abs().max().item()
+    err_r = (exact_t - exact).abs().max().item() / exact.abs().max().item()
+    print(f"tf32 gemm (rna-rounded operands): vs rounded-exact {err_t:.3e}; rounding itself {err_r:.3e}")
+    assert err_t < 2e-5 and err_r < 1e-3
+
+
+def test_gemm_skinny_shapes_fall_to_simt(ops, ref):
+    ops.set_gemm_impl(0)
+    for (M, N, K) in [(2500, 1, 400), (2500, 18, 400), (777, 1000, 18)]:
+        A, B = rnd(M, K, seed=1), rnd(N, K, seed=2)
+        C, Cr = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+        ops.gemm(A, B, C); ref.gemm(A, B, Cr)
+        close(C, Cr, rtol=1e-5, what=f"skinny {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N", [(50, 1000), (2500, 400), (7, 1000), (1000, 33)])
+def test_ln_elu_fwd_bwd(ops, ref, M, N):
+    x, gamma, beta, dy = rnd(M, N, scale=2.0), rnd(N) * 0.5 + 1, rnd(N, seed=3) * 0.1, rnd(M, N, seed=5)
+    out = {}
+    for name, o in (("n", ops), ("r", ref)):
+        y, mean, rstd = torch.empty(M, N, device=DEV), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+        o.ln_elu_fwd(x, gamma, beta, 1e-3, y, mean, rstd)
+        dx = torch.empty(M, N, device=DEV)
+        dg, db, dbias = (torch.zeros(N, device=DEV) for _ in range(3))
+        o.ln_elu_bwd(dy, x, y, gamma, mean, rstd, dx, dg, db, dbias)
+        out[name] = (y, mean, rstd, dx, dg, db, dbias)
+    # vs torch autograd as well
+    xa = x.clone().requires_grad_(True); ga = gamma.clone().requires_grad_(True); ba = beta.clone().requires_grad_(True)
+    ya = torch.nn.functional.elu(torch.nn.functional.layer_norm(xa, (N,), ga, ba, 1e-3))
+    ya.backward(dy)
+    close(out["n"][0], ya.detach(), 1e-5, 1e-6, "ln y vs torch")
+    close(out["n"][3], xa.grad, 2e-5, 1e-6, "ln dx vs torch")
+    close(out["n"][4], ga.grad, 5e-5, 1e-5, "ln dgamma vs torch")
+    close(out["n"][5], ba.grad, 5e-5, 1e-5, "ln dbeta vs torch")
+    for a, b, w in zip(out["n"], out["r"], ("y", "mean", "rstd", "dx", "dgamma", "dbeta", "dbias")):
+        close(a, b, 5e-5, 1e-5, "ln " + w)
+
+
+@pytest.mark.parametrize("M,D", [(50, 2048), (333, 64)])
+def test_gru_fwd_bwd(ops, ref, M, D):
+    gi, gh, hp = rnd(M, 3 * D), rnd(M, 3 * D, seed=1), torch.tanh(rnd(M, D, seed=2))
+    mask = (torch.rand(M, device=DEV) > 0.3).float()
+    dh_a, dh_b = rnd(M, D, seed=3), rnd(M, D, seed=4)
+    res = {}
+    for name, o in (("n", ops), ("r", ref)):
+        hout, hm, gates = torch.empty(M, D, device=DEV), torch.empty(M, D, device=DEV), torch.empty(M, 4 * D, device=DEV)
+        o.gru_fwd(gi, gh, hp, hout, hm, mask, gates)
+        dgi, dgh, dc = torch.empty(M, 3 * D, device=DEV), torch.empty(M, 3 * D, device=DEV), torch.empty(M, D, device=DEV)
+        o.gru_bwd(dh_a, dh_b, mask, gates, hp, dgi, dgh, dc)
+        res[name] = (hout, hm, gates, dgi, dgh, dc)
+    cell = torch.nn.GRUCell(8, D).to(DEV)   # formula check against torch's own fused cell
+    gia, gha, hpa = gi.clone().requires_grad_(True), gh.clone().requires_grad_(True), hp.clone().requires_grad_(True)
+    r = torch.sigmoid(gia[:, :D] + gha[:, :D]); u = torch.sigmoid(gia[:, D:2 * D] + gha[:, D:2 * D])
+    n = torch.tanh(gia[:, 2 * D:] + r * gha[:, 2 * D:]); hy = n + u * (hpa - n)
+    hy.backward(dh_a + dh_b * mask[:, None])
+    close(res["n"][0], hy.detach(), 1e-5, 1e-6, "gru h")
+    close(res["n"][3], gia.grad, 2e-5, 1e-6, "gru dgi")
+    close(res["n"][4], gha.grad, 2e-5, 1e-6, "gru dgh")
+    for a, b, w in zip(res["n"], res["r"], ("h", "hmask", "gates", "dgi", "dgh", "dcarry")):
+        close(a, b, 2e-5, 1e-6, "gru " + w)
+
+
+@pytest.mark.parametrize("M,G,C", [(50, 32, 32), (2500, 32, 32), (2500, 1, 18), (100, 4, 7)])
+def test_cat_sample_bit_exact_and_st_bwd(ops, ref, M, G, C):
+    logits = rnd(M, G * C, scale=2.0)
+    noise = torch.empty(M, G * C, device=DEV).exponential_()
+    mask = (torch.rand(M, device=DEV) > 0.3).float()
+    res = {}
+    for name, o in (("n", ops), ("r", ref)):
+        z, zm = torch.empty(M, G * C, device=DEV), torch.empty(M, G * C, device=DEV)
+        idx = torch.empty(M, G, dtype=torch.int32, device=DEV)
+        o.cat_sample(logits, noise, G, C, z, zm, mask, idx)
+        res[name] = (z, zm, idx)
+    # the oracle definition: torch's own formulation
+    l3 = logits.view(M, G, C)
+    probs = torch.distributions.OneHotCategorical(logits=l3).probs
+    k = (probs / noise.view(M, G, C)).argmax(-1)
+    mism = (res["n"][2].long() != k).sum().item()
+    assert mism == 0, f"{mism} / {M * G} sampled indices differ from argmax(probs/q)"
+    assert torch.equal(res["n"][0], res["r"][0]) and torch.equal(res["n"][1], res["r"][1])
+    dz_a, dz_b, extra, rs = rnd(M, G * C, seed=1), rnd(M, G * C, seed=2), rnd(M, G * C, seed=3), torch.rand(M, device=DEV)
+    dn, dr = torch.empty(M, G * C, device=DEV), torch.empty(M, G * C, device=DEV)
+    ops.cat_st_bwd(logits, G, C, dz_a, dz_b, mask, extra, rs, 0.1, dn)
+    ref.cat_st_bwd(logits, G, C, dz_a, dz_b, mask, extra, rs, 0.1, dr)
+    close(dn, dr, 2e-5, 1e-6, "st bwd")
+    la = logits.clone().requires_grad_(True)
+    pa = torch.softmax(la.view(M, G, C), -1).view(M, G * C)
+    pa.backward(dz_a + dz_b * mask[:, None])
+    close(dn - 0.1 * rs[:, None] * extra, la.grad, 5e-5, 1e-6, "st bwd vs autograd")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_kl(ops, ref, mode):
+    M, G, C = 300, 32, 32
+    post, prior = rnd(M, G * C, scale=1.5), rnd(M, G * C, scale=1.5, seed=1)
+    idx = torch.randint(0, C, (M, G), device=DEV, dtype=torch.int32)
+    res = {}
+    for name, o in (("n", ops), ("r", ref)):
+        v = [torch.empty(M, device=DEV) for _ in range(4)] + [torch.empty(M, G * C, device=DEV) for _ in range(2)]
+        o.kl(post, prior, idx, mode, 0.8, G, C, *v)
+        res[name] = v
+    for a, b, w in zip(res["n"], res["r"], ("loss_kl", "kl_exact", "ent_post", "ent_prior", "dpost", "dprior")):
+        close(a, b, 3e-5, 1e-5, "kl " + w)
+    if mode == 0:  # against torch.distributions + autograd (dreamer.py:328-339)
+        import torch.distributions as D
+        pa, qa = post.clone().requires_grad_(True), prior.clone().requires_grad_(True)
+        d = lambda x: D.Independent(D.OneHotCategoricalStraightThrough(logits=x.view(M, G, C)), 1)
+        loss = 0.2 * D.kl.kl_divergence(d(pa), d(qa.detach())) + 0.8 * D.kl.kl_divergence(d(pa.detach()), d(qa))
+        loss.sum().backward()
+        close(res["n"][0], loss.detach(), 3e-5, 1e-5, "kl vs torch")
+        close(res["n"][4], pa.grad, 5e-5, 1e-6, "dpost vs torch")
+        close(res["n"][5], qa.grad, 5e-5, 1e-6, "dprior vs torch")
+        close(res["n"][2], d(post).entropy(), 3e-5, 1e-5, "entropy")
+
+
+def test_conv_data_movement_against_torch_conv(ops, ref):
+    NB, Cin, Cout, k = 6, 5, 8, 4
+    x = rnd(NB, Cin, 14, 14)
+    w = rnd(Cout, Cin, k, k, seed=1)
+    b = rnd(Cout, seed=2)
+    yref = torch.nn.functional.conv2d(x, w, b, stride=2)                     # (NB,Cout,6,6)
+    for korder in (0, 1):
+        col = torch.empty(NB * 36, k * k * Cin, device=DEV)
+        ops.im2col(x.permute(0, 2, 3, 1), k, korder, col, round_out=False)
+        colr = torch.empty_like(col)
+        ref.im2col(x.permute(0, 2, 3, 1), k, korder, colr)
+        assert torch.equal(col, colr)
+        wk = (w.permute(0, 2, 3, 1) if korder == 0 else w).reshape(Cout, -1).contiguous()
+        y = torch.empty(NB * 36, Cout, device=DEV)
+        ops.set_gemm_impl(1)
+        ops.gemm(col, wk, y, bias=b)
+        close(y.view(NB, 6, 6, Cout).permute(0, 3, 1, 2), yref, 1e-5, 1e-5, f"conv korder {korder}")
+    # transposed conv = gemm + col2im  (decoders.py:149-155)
+    wt = rnd(Cout, Cin, 5, 5, seed=3)   # ConvTranspose2d weight (in=Cout, out=Cin)
+    bt = rnd(Cin, seed=4)
+    xin = rnd(NB, Cout, 6, 6, seed=5)
+    yt = torch.nn.functional.conv_transpose2d(xin, wt, bt, stride=2)           # (NB,Cin,15,15)
+    wtp = wt.permute(2, 3, 1, 0).reshape(25 * Cin, Cout).contiguous()
+    cols = torch.empty(NB * 36, 25 * Cin, device=DEV)
+    ops.gemm(xin.permute(0, 2, 3, 1).reshape(NB * 36, Cout).contiguous(), wtp, cols)
+    out = torch.empty(NB, 15, 15, Cin, device=DEV)
+    ops.col2im(cols, 6, 6, 5, bt, 0, out, round_out=False)
+    close(out.permute(0, 3, 1, 2), yt, 1e-5, 1e-5, "convT via col2im")
+    outr = torch.empty_like(out)
+    ref.col2im(cols, 6, 6, 5, bt, 0, outr)
+    close(out, outr, 1e-6, 1e-6, "col2im vs ref")
+    # output extent larger than the taps reach (conv input-grad for odd sizes): zero fill + ELU
+    out2, out2r = torch.empty(NB, 16, 16, Cin, device=DEV), torch.empty(NB, 16, 16, Cin, device=DEV)
+    ops.col2im(cols, 6, 6, 5, None, 1, out2, round_out=False); ref.col2im(cols, 6, 6, 5, None, 1, out2r)
+    close(out2, out2r, 1e-6, 1e-6, "col2im padded extent")
+    # fused image loss
+    tgt = rnd(NB // 2, Cin, 15, 15, seed=6)
+    r = {}
+    for name, o in (("n", ops), ("r", ref)):
+        dec, diff = torch.empty(NB, Cin, 15, 15, device=DEV), torch.empty(NB, Cin, 15, 15, device=DEV)
+        loss, cs = torch.empty(NB, device=DEV), torch.empty(NB, Cin, device=DEV)
+        o.col2im_imgloss(cols, NB, 6, 6, Cin, 5, bt, tgt, 2, dec, diff, loss, cs)
+        r[name] = (dec, diff, loss, cs)
+    for a, b_, w_ in zip(r["n"], r["r"], ("dec", "diff", "loss", "csum")):
+        close(a, b_, 2e-5, 1e-5, "imgloss " + w_)
+    ops.set_gemm_impl(0)
+
+
+def test_bias_act_bwd_permute_small_ops(ops, ref):
+    M, N = 5000, 48
+    y = torch.nn.functional.elu(rnd(M, N))
+    dy = rnd(M, N, seed=1)
+    a, b = dy.clone(), dy.clone()
+    da, db = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV)
+    ops.bias_act_bwd(a, y, 1, da); ref.bias_act_bwd(b, y, 1, db)
+    close(a, b, 1e-6, 1e-7, "act bwd"); close(da, db, 1e-4, 1e-4, "bias grad")
+    x = rnd(7, 5, 4, 3)
+    for perm in [(0, 2, 3, 1), (2, 3, 1, 0), (0, 3, 1, 2), (3, 2, 0, 1)]:
+        o1 = torch.empty([x.shape[p] for p in perm], device=DEV)
+        ops.permute4(x, o1, perm)
+        assert torch.equal(o1, x.permute(*perm).contiguous())
+        o2 = o1.clone(); ops.permute4(x, o2, perm, accumulate=True)
+        assert torch.equal(o2, 2 * o1)
+    m = torch.rand(M, device=DEV)
+    o1 = torch.empty(M, N, device=DEV); ops.mask_rows(dy, m, o1); close(o1, dy * m[:, None], 1e-6)
+    z = dy.clone(); ops.rowscale(z, m[: M // 4], 4, 0.5); close(z, dy * 0.5 * m[: M // 4].repeat_interleave(4)[:, None], 1e-6)
+    gs = torch.empty(M // 4, N, device=DEV); ops.group_sum(dy, 4, gs); close(gs, dy.view(M // 4, 4, N).sum(1), 1e-5, 1e-6)
+    cs = torch.zeros(N, device=DEV); ops.colsum(dy, cs); close(cs, dy.sum(0), 1e-4, 1e-4)
+    reset = torch.rand(5, 7, device=DEV) > 0.5
+    mk = torch.empty(5, 21, device=DEV); ops.reset_mask(reset, 3, mk)
+    assert torch.equal(mk.view(5, 7, 3), (~reset).float()[:, :, None].expand(5, 7, 3))
+
+
+@pytest.mark.parametrize("I", [1, 4])
+def test_losses_and_wm_loss(ops, ref, I):
+    TB = 120; N = TB * I
+    y, tgt = rnd(N), torch.tanh(rnd(TB, seed=1))
+    tb01 = (torch.rand(TB, device=DEV) > 0.9).float()
+    for kind, t in ((0, tgt), (1, tb01)):
+        r = {}
+        for name, o in (("n", ops), ("r", ref)):
+            v = [torch.empty(N, device=DEV) for _ in range(3)]
+            o.scalar_head_loss(kind, y, t, I, *v); r[name] = v
+        for a, b in zip(r["n"], r["r"]):
+            close(a, b, 1e-5, 1e-6, f"head loss {kind}")
+    ls = [torch.rand(N, device=DEV) * s for s in (100, 1, 1, 20, 20, 100, 100)]
+    r = {}
+    for name, o in (("n", ops), ("r", ref)):
+        w, tb = torch.empty(N, device=DEV), torch.empty(TB, 8, device=DEV)
+        o.wm_loss(TB, I, 0.1, 1.0, 1.0, 1.0, *ls, w, tb)
+        mean = torch.empty(8, device=DEV); o.colmean(tb, mean)
+        r[name] = (w, tb, mean)
+    for a, b, nm in zip(r["n"], r["r"], ("w", "tb", "mean")):
+        close(a, b, 2e-5, 1e-6, "wm_loss " + nm)
+
+
+def test_actor_critic_kernels(ops, ref):
+    H, Md, A = 15, 700, 18
+    J = H + 1
+    vt, v, rew, tl = rnd(J * Md), rnd(J * Md, seed=1), rnd(J * Md, seed=2), rnd(J * Md, seed=3) - 3
+    r = {}
+    for name, o in (("n", ops), ("r", ref)):
+        term = torch.empty(J * Md, device=DEV)
+        outs = [torch.empty(H * Md, device=DEV) for _ in range(5)]
+        sums = torch.zeros(8, dtype=torch.float64, device=DEV)
+        o.gae_critic(H, Md, 0.99, 0.95, vt, v, rew, tl, term, *outs, sums)
+        r[name] = [term] + outs + [sums]
+    for a, b, nm in zip(r["n"], r["r"], ("term", "adv", "agae", "target", "weight", "dv", "sums")):
+        close(a, b, 3e-5, 1e-6, "gae " + nm)
+    logits = rnd(H * Md, A)
+    acts = torch.nn.functional.one_hot(torch.randint(0, A, (H * Md,), device=DEV), A).float()
+    ag, w = r["r"][2], r["r"][4]
+    res = {}
+    for name, o in (("n", ops), ("r", ref)):
+        dl = torch.zeros(H * Md, A, device=DEV); s = torch.zeros(2, dtype=torch.float64, device=DEV)
+        o.actor_loss_onehot(1e-3, logits, acts, ag, w, dl, s); res[name] = (dl, s)
+    close(res["n"][0], res["r"][0], 3e-5, 1e-9, "actor dlogits"); close(res["n"][1], res["r"][1], 1e-5, 1e-6, "actor sums")
+    # tanh_normal
+    Ac = 12
+    out = rnd(H * Md, 2 * Ac)
+    eps = torch.randn(H * Md, Ac, device=DEV)
+    an, ar = torch.empty(H * Md, Ac, device=DEV), torch.empty(H * Md, Ac, device=DEV)
+    ops.tanh_normal_sample(out, eps, an); ref.tanh_normal_sample(out, eps, ar)
+    close(an, ar, 1e-5, 1e-6, "tanh_normal sample")
+    res = {}
+    for name, o in (("n", ops), ("r", ref)):
+        dl = torch.zeros(H * Md, 2 * Ac, device=DEV); s = torch.zeros(2, dtype=torch.float64, device=DEV)
+        o.actor_loss_tanh_normal(1e-4, out, ar, ag, w, dl, s); res[name] = (dl, s)
+    close(res["n"][0], res["r"][0], 2e-3, 1e-9, "tanh_normal dout")   # atanh near |a|->1 amplifies ulps
+    close(res["n"][1], res["r"][1], 1e-4, 1e-4, "tanh_normal sums")
+
+
+def test_optimizer_kernels_against_torch_adamw(ops):
+    n = 1_000_003
+    p0, g = rnd(n), rnd(n, scale=3.0, seed=1)
+    ss = torch.zeros(1, device=DEV); ops.sumsq(g, ss)
+    close(ss, (g.double() ** 2).sum().float().view(1), 1e-4, 0, "sumsq")
+    gc = g.clone(); norm = torch.empty(1, device=DEV)
+    ops.clip_scale(gc, ss, 200.0, norm)
+    gt = g.clone().requires_grad_(False)
+    pt = torch.nn.Parameter(p0.clone()); pt.grad = g.clone()
+    tn = torch.nn.utils.clip_grad_norm_([pt], 200.0)
+    close(norm, tn.view(1), 1e-4, 0, "norm"); close(gc, pt.grad, 1e-4, 1e-7, "clipped grad")
+    opt = torch.optim.AdamW([pt], lr=3e-4, eps=1e-5)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(3):
+        opt.step()
+        ops.inc(step)
+        ops.adamw(p, gc, m, v, 3e-4, 0.9, 0.999, 1e-5, 0.01, step)
+    close(p, pt.detach(), 1e-5, 1e-6, "adamw params after 3 steps")
