@@ -12,9 +12,11 @@
 // Operand layouts: both operands may be K-major ([rows][K], K contiguous) or MN-major ([K][rows]);
 // the second form lets the backward contractions dX = dY*W and dW = dY^T*X read the forward tensors
 // in place (no transposes in HBM).  Smem tiles follow the canonical UMMA layouts
-// (K-major:  8-row x 128 B swizzle atoms, SBO = 1024 B;
-//  MN-major: 32-element x 8-k atoms,      LBO = 4096 B between 32-wide MN groups, SBO = 1024 B).
+// (K-major:  8-row x 128 B SWIZZLE_128B atoms, SBO = 1024 B;
+//  MN-major: 32-element x 4-k SWIZZLE_128B_BASE32B atoms (TMA SWIZZLE_128B_ATOM_32B), LBO = 4096 B between
+//            32-wide MN groups, SBO = 512 B between 4-row k groups).
 #include "pd_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -35,6 +37,7 @@ struct GemmArgs {
     int M, N, K;
     int a_mn, b_mn;
     int num_m, num_n, splits, kb_total, kb_per_split;
+    uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
     PdEpilogue epi;
 };
 
@@ -103,13 +106,15 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[3
 
 // UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B — the only layout tcgen05 accepts for
+// MN-major 32-bit (tf32) operands (cutlass sm100_common.inl:88-93): 32-byte chunks swizzled over 4 k-rows.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
 }
 
@@ -207,10 +212,12 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t sb = sa + A_BYTES;
 #pragma unroll
                     for (int s = 0; s < BK / UMMA_K; ++s) {
-                        const uint64_t ad = g.a_mn ? make_desc(sa + s * 1024, 4096, 1024)
-                                                   : make_desc(sa + s * 32, 16, 1024);
-                        const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, 4096, 1024)
-                                                   : make_desc(sb + s * 32, 16, 1024);
+                        // MN-major: 8 k-rows per MMA = two 4-row (512 B) swizzle atoms, SBO apart;
+                        //           LBO = 4096 B between 32-element MN groups (one TMA box each).
+                        const uint64_t ad = g.a_mn ? make_desc(sa + s * 1024, g.mn_lbo, g.mn_sbo, 1)
+                                                   : make_desc(sa + s * 32, 16, 1024, 2);
+                        const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, g.mn_lbo, g.mn_sbo, 1)
+                                                   : make_desc(sb + s * 32, 16, 1024, 2);
                         tc_mma_tf32(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
@@ -287,14 +294,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D fp32 tensor map: dim0 = contiguous dimension.
 int make_map(pd_handle* h, CUtensorMap* tm, const float* base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems,
-             uint32_t box0, uint32_t box1) {
+             uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
     cuuint64_t gdim[2] = {dim0, dim1};
     cuuint64_t gstride[1] = {ld_elems * 4};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride,
                                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu", (int)r,
                                    (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)ld_elems);
@@ -315,11 +322,11 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     }
     CUtensorMap tmA, tmB;
     int rc;
-    if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
-    else       rc = make_map(h, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BK);
+    if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else       rc = make_map(h, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (!b_mn) rc = make_map(h, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
-    else       rc = make_map(h, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BK);
+    if (!b_mn) rc = make_map(h, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    else       rc = make_map(h, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
 
     GemmArgs g;
@@ -327,6 +334,11 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
     g.kb_total = pd_cdiv(K, BK);
     g.epi = epi;
+    g.mn_lbo = 4096; g.mn_sbo = 512;
+    if (const char* dbg = getenv("PD_GEMM_MN_DESC")) {   // bring-up aid: "lbo,sbo" in bytes
+        unsigned a = 0, b = 0;
+        if (sscanf(dbg, "%u,%u", &a, &b) == 2) { g.mn_lbo = a; g.mn_sbo = b; }
+    }
     int tiles = g.num_m * g.num_n;
     int splits = 1;
     if (epi.accumulate && tiles < h->num_sms) {

@@ -1,0 +1,919 @@
+"""Drop-in `Dreamer` module: the reference's API (pydreamer/models/dreamer.py:19-230) over hand-written
+sm_100a kernels.
+
+What is kept from the reference contract:
+  * ctor `Dreamer(conf)` with the reference's config keys; an nn.Module whose state_dict keys and
+    shapes equal the reference's, so checkpoints round-trip with an unmodified reference Dreamer;
+  * `init_state`, `training_step` (same arguments, same 5-tuple, same dict keys), `init_optimizers`
+    (same tuple order), `grad_clip` (same dict keys); each returned loss is backwarded separately by
+    the caller exactly as train.py:184-187 does.
+
+What is different inside: the whole step — forward AND backward — is an explicit schedule of kernels
+from libpd_b200.so (no autograd tape, no torch math).  `training_step` computes the gradients of the
+four losses directly into a flat fp32 gradient arena; the returned loss tensors are connected to the
+parameters through a tiny autograd.Function whose backward hands those precomputed gradients over,
+so `loss.backward()` in the caller works unchanged.  Parameters live in one flat arena (views), which
+is what the fused optimizer and the single-bucket data-parallel all-reduce operate on.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import ops as _ops
+from .ops import ACT_ELU, ACT_NONE
+
+
+# ======================================================================================
+# parameter containers (names/shapes identical to the reference's module tree)
+# ======================================================================================
+def _mlp_seq(in_dim, out_dim, hidden_dim, hidden_layers, layer_norm):
+    """common.py:37-65"""
+    if not layer_norm:
+        raise NotImplementedError("layer_norm=False is outside the accelerated path (SURVEY.md §8f N4)")
+    layers, dim = [], in_dim
+    for _ in range(hidden_layers):
+        layers += [nn.Linear(dim, hidden_dim), nn.LayerNorm(hidden_dim, eps=1e-3), nn.ELU()]
+        dim = hidden_dim
+    layers += [nn.Linear(dim, out_dim)]
+    if out_dim == 1:
+        layers += [nn.Flatten(0)]
+    return nn.Sequential(*layers)
+
+
+class _MLP(nn.Module):
+    def __init__(self, in_dim, out_dim, hidden_dim, hidden_layers, layer_norm):
+        super().__init__()
+        self.in_dim, self.out_dim, self.hidden_dim, self.hidden_layers = in_dim, out_dim, hidden_dim, hidden_layers
+        self.model = _mlp_seq(in_dim, out_dim, hidden_dim, hidden_layers, layer_norm)
+
+
+class _DenseHead(nn.Module):
+    """decoders.py:257-319 (DenseBernoulliDecoder / DenseNormalDecoder): `.model` is an MLP"""
+
+    def __init__(self, in_dim, hidden_layers, layer_norm, hidden_dim=400):
+        super().__init__()
+        self.model = _MLP(in_dim, 1, hidden_dim, hidden_layers, layer_norm)
+
+
+class _ConvEncoder(nn.Module):
+    """encoders.py:72-96"""
+
+    def __init__(self, in_channels, d):
+        super().__init__()
+        self.out_dim = d * 32
+        self.model = nn.Sequential(nn.Conv2d(in_channels, d, 4, 2), nn.ELU(), nn.Conv2d(d, d * 2, 4, 2), nn.ELU(),
+                                   nn.Conv2d(d * 2, d * 4, 4, 2), nn.ELU(), nn.Conv2d(d * 4, d * 8, 4, 2), nn.ELU(),
+                                   nn.Flatten())
+
+
+class _MultiEncoder(nn.Module):
+    def __init__(self, conf):
+        super().__init__()
+        if conf.image_encoder != "cnn" or conf.reward_input or conf.vecobs_size:
+            raise NotImplementedError("accelerated path covers image_encoder=cnn without reward_input/vecobs "
+                                      "(SURVEY.md §2 row 4); use the reference for other encoders")
+        self.encoder_image = _ConvEncoder(conf.image_channels, conf.cnn_depth)
+        self.out_dim = self.encoder_image.out_dim
+
+
+class _ConvDecoder(nn.Module):
+    """decoders.py:111-161"""
+
+    def __init__(self, in_dim, out_channels, d):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(in_dim, d * 32), nn.Unflatten(-1, (d * 32, 1, 1)),
+                                   nn.ConvTranspose2d(d * 32, d * 4, 5, 2), nn.ELU(),
+                                   nn.ConvTranspose2d(d * 4, d * 2, 5, 2), nn.ELU(),
+                                   nn.ConvTranspose2d(d * 2, d, 6, 2), nn.ELU(),
+                                   nn.ConvTranspose2d(d, out_channels, 6, 2))
+
+
+class _MultiDecoder(nn.Module):
+    def __init__(self, features_dim, conf):
+        super().__init__()
+        if conf.image_decoder != "cnn" or conf.reward_decoder_categorical or conf.vecobs_size:
+            raise NotImplementedError("accelerated path covers image_decoder=cnn + Normal reward head "
+                                      "(SURVEY.md §2 row 5)")
+        if conf.image_size != 64:
+            raise NotImplementedError("conv geometry is the reference's 64x64 one (encoders.py:77-90)")
+        self.image = _ConvDecoder(features_dim, conf.image_channels, conf.cnn_depth)
+        self.reward = _DenseHead(features_dim, conf.reward_decoder_layers, conf.layer_norm)
+        self.terminal = _DenseHead(features_dim, conf.terminal_decoder_layers, conf.layer_norm)
+
+
+class _GRUStack(nn.Module):
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.GRUCell(input_size, hidden_size)])
+
+
+class _RSSMCell(nn.Module):
+    """rssm.py:96-116"""
+
+    def __init__(self, embed_dim, action_dim, deter_dim, stoch_dim, stoch_discrete, hidden_dim):
+        super().__init__()
+        z = stoch_dim * stoch_discrete
+        self.z_mlp = nn.Linear(z, hidden_dim)
+        self.a_mlp = nn.Linear(action_dim, hidden_dim, bias=False)
+        self.in_norm = nn.LayerNorm(hidden_dim, eps=1e-3)
+        self.gru = _GRUStack(hidden_dim, deter_dim)
+        self.prior_mlp_h = nn.Linear(deter_dim, hidden_dim)
+        self.prior_norm = nn.LayerNorm(hidden_dim, eps=1e-3)
+        self.prior_mlp = nn.Linear(hidden_dim, z)
+        self.post_mlp_h = nn.Linear(deter_dim, hidden_dim)
+        self.post_mlp_e = nn.Linear(embed_dim, hidden_dim, bias=False)
+        self.post_norm = nn.LayerNorm(hidden_dim, eps=1e-3)
+        self.post_mlp = nn.Linear(hidden_dim, z)
+
+
+class _RSSMCore(nn.Module):
+    def __init__(self, *a):
+        super().__init__()
+        self.cell = _RSSMCell(*a)
+
+
+def _init_weights_tf2(m):
+    """functions.py:81-94"""
+    if type(m) in (nn.Conv2d, nn.ConvTranspose2d, nn.Linear):
+        nn.init.xavier_uniform_(m.weight.data)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias.data)
+    if type(m) == nn.GRUCell:
+        nn.init.xavier_uniform_(m.weight_ih.data)
+        nn.init.orthogonal_(m.weight_hh.data)
+        nn.init.zeros_(m.bias_ih.data)
+        nn.init.zeros_(m.bias_hh.data)
+
+
+class _WorldModel(nn.Module):
+    """dreamer.py:232-284"""
+
+    def __init__(self, conf):
+        super().__init__()
+        if not conf.stoch_discrete:
+            raise NotImplementedError("Gaussian latents (stoch_discrete=0) are outside the accelerated path (§8f N4)")
+        if conf.gru_layers != 1 or conf.gru_type != "gru":
+            raise NotImplementedError("accelerated path covers gru_type=gru, gru_layers=1 (SURVEY.md §2 row 3)")
+        if conf.aux_critic:
+            raise NotImplementedError("aux_critic is outside the accelerated path")
+        if conf.stoch_discrete > 32 or conf.stoch_dim > 32:
+            raise NotImplementedError("categorical kernels handle <= 32 groups of <= 32 classes")
+        self.encoder = _MultiEncoder(conf)
+        features_dim = conf.deter_dim + conf.stoch_dim * conf.stoch_discrete
+        self.decoder = _MultiDecoder(features_dim, conf)
+        self.core = _RSSMCore(self.encoder.out_dim, conf.action_dim, conf.deter_dim, conf.stoch_dim,
+                              conf.stoch_discrete, conf.hidden_dim)
+        for m in self.modules():
+            _init_weights_tf2(m)
+
+
+class _ActorCritic(nn.Module):
+    """a2c.py:11-41"""
+
+    def __init__(self, in_dim, out_actions, layer_norm, actor_dist, hidden_dim=400, hidden_layers=4):
+        super().__init__()
+        actor_out = out_actions if actor_dist == "onehot" else 2 * out_actions
+        self.actor = _MLP(in_dim, actor_out, hidden_dim, hidden_layers, layer_norm)
+        self.critic = _MLP(in_dim, 1, hidden_dim, hidden_layers, layer_norm)
+        self.critic_target = _MLP(in_dim, 1, hidden_dim, hidden_layers, layer_norm)
+        self.critic_target.requires_grad_(False)
+        self.train_steps = 0
+
+
+class _NoProbeHead(nn.Module):
+    """probes.py:140-150"""
+
+    def __init__(self):
+        super().__init__()
+        self.dummy = nn.Parameter(torch.zeros(1), requires_grad=True)
+
+
+# ======================================================================================
+# loss <-> precomputed-gradient bridge
+# ======================================================================================
+class _AttachGrads(torch.autograd.Function):
+    """Returns `value` as a differentiable scalar whose backward delivers the gradients that the kernel
+    schedule already wrote into the arena group `gid` (scaled by the incoming grad_output)."""
+
+    @staticmethod
+    def forward(ctx, value, owner, gid, *params):
+        ctx.owner, ctx.gid = owner, gid
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.owner._deliver_grads(ctx.gid, grad_out)
+        return (None, None, None) + tuple(None for _ in ctx.owner._group_params[ctx.gid])
+
+
+class _FusedAdamW:
+    """One optimizer of the tuple `init_optimizers` returns (dreamer.py:60-71): torch.optim.AdamW
+    semantics (decoupled weight_decay=0.01, eps, no amsgrad) over one contiguous arena group."""
+
+    def __init__(self, owner, gid, lr, eps, betas=(0.9, 0.999), weight_decay=0.01):
+        self.owner, self.gid = owner, gid
+        self.defaults = dict(lr=lr, eps=eps, betas=betas, weight_decay=weight_decay)
+        self.param_groups = [dict(params=list(owner._group_params[gid]), **self.defaults)]
+        self._alloc()
+
+    def _alloc(self):
+        a = self.owner._group_slice(self.gid, self.owner._arena)
+        self.exp_avg = torch.zeros_like(a)
+        self.exp_avg_sq = torch.zeros_like(a)
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=a.device)
+
+    def zero_grad(self, set_to_none=True):
+        # gradients are overwritten (not accumulated) by every training_step; nothing to clear
+        return None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        o = self.owner
+        o._ensure_arena()
+        p = o._group_slice(self.gid, o._arena)
+        g = o._group_slice(self.gid, o._garena)
+        if self.exp_avg.device != p.device:
+            self._alloc()
+        pg = self.param_groups[0]
+        o.ops.inc(self.step_t)
+        o.ops.adamw(p, g, self.exp_avg, self.exp_avg_sq, pg["lr"], pg["betas"][0], pg["betas"][1], pg["eps"],
+                    pg["weight_decay"], self.step_t)
+        o._weights_dirty = True
+
+    def state_dict(self):
+        return dict(state=dict(exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, step=self.step_t),
+                    param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+
+    def load_state_dict(self, sd):
+        st = sd["state"]
+        self.exp_avg.copy_(st["exp_avg"]); self.exp_avg_sq.copy_(st["exp_avg_sq"]); self.step_t.copy_(st["step"])
+        for k, v in sd["param_groups"][0].items():
+            self.param_groups[0][k] = v
+
+
+# ======================================================================================
+# the module
+# ======================================================================================
+GROUPS = ("wm", "probe", "actor", "critic")
+
+
+class Dreamer(nn.Module):
+
+    def __init__(self, conf):
+        super().__init__()
+        assert conf.action_dim > 0, "Need to set action_dim to match environment"   # dreamer.py:23
+        if conf.probe_model != "none":
+            raise NotImplementedError("probe heads are research probes outside the hot path (SURVEY.md §2 row 9)")
+        if conf.probe_gradients:
+            raise NotImplementedError("probe_gradients is for the baselines (SURVEY.md §2 row 10)")
+        if conf.actor_dist not in ("onehot", "tanh_normal"):
+            raise NotImplementedError(f"actor_dist={conf.actor_dist}")
+        if conf.actor_grad != "reinforce":
+            raise NotImplementedError("actor_grad=dynamics asserts upstream at a2c.py:131 (SURVEY.md §0.5); "
+                                      "the accelerated path implements reinforce")
+        self.conf = conf
+        self.iwae_samples = conf.iwae_samples
+        self.imag_horizon = conf.imag_horizon
+        self.probe_gradients = conf.probe_gradients
+        features_dim = conf.deter_dim + conf.stoch_dim * conf.stoch_discrete
+        self.wm = _WorldModel(conf)
+        self.ac = _ActorCritic(features_dim, conf.action_dim, conf.layer_norm, conf.actor_dist)
+        self.probe_model = _NoProbeHead()
+        # static dims
+        self.d = SimpleNamespace(D=conf.deter_dim, G=conf.stoch_dim, C=conf.stoch_discrete,
+                                 Z=conf.stoch_dim * conf.stoch_discrete, Hd=conf.hidden_dim, E=self.wm.encoder.out_dim,
+                                 A=conf.action_dim, F=features_dim, cd=conf.cnn_depth, IC=conf.image_channels,
+                                 Aout=conf.action_dim if conf.actor_dist == "onehot" else 2 * conf.action_dim)
+        self._arena = None
+        self._arena_device = None
+        self._ws = {}
+        self._ops = None
+        self._weights_dirty = True
+        self._dp = None           # optional data-parallel reducer (pydreamer_b200.parallel)
+        self._build_registry()
+
+    # ------------------------------------------------------------------ arena
+    def _build_registry(self):
+        self._group_params = {
+            "wm": list(self.wm.parameters()),
+            "probe": list(self.probe_model.parameters()),
+            "actor": list(self.ac.actor.parameters()),
+            "critic": list(self.ac.critic.parameters()),
+            "target": list(self.ac.critic_target.parameters()),
+        }
+        self._names = {id(p): n for n, p in self.named_parameters()}
+        off = 0
+        self._offsets, self._group_range = {}, {}
+        for gname in GROUPS + ("target",):
+            start = off
+            for p in self._group_params[gname]:
+                self._offsets[id(p)] = off
+                off += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned (TMA)
+            self._group_range[gname] = (start, off)
+        self._arena_numel = off
+        self._train_numel = self._group_range["critic"][1]
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._arena = None   # .to()/.cuda() re-created the tensors: re-flatten lazily
+        return r
+
+    def _ensure_arena(self):
+        p0 = next(self.parameters())
+        if self._arena is not None and self._arena_device == p0.device and p0.data_ptr() == self._arena.data_ptr():
+            return
+        dev = p0.device
+        arena = torch.zeros(self._arena_numel, dtype=torch.float32, device=dev)
+        garena = torch.zeros(self._train_numel, dtype=torch.float32, device=dev)
+        for g in GROUPS + ("target",):
+            for p in self._group_params[g]:
+                o = self._offsets[id(p)]
+                v = arena[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                if g != "target":
+                    p.grad = garena[o:o + p.numel()].view(p.shape)
+        self._arena, self._garena, self._arena_device = arena, garena, dev
+        self._sarena = torch.zeros_like(arena)     # tf32-rounded shadow of the arena (GEMM operands)
+        self._ws = {}
+        self._ops = None
+        self._weights_dirty = True
+
+    def _group_slice(self, gid, arena):
+        a, b = self._group_range[gid]
+        return arena[a:b]
+
+    @property
+    def ops(self):
+        if self._ops is None:
+            self._ops = _ops.get_ops(next(self.parameters()).device)
+        return self._ops
+
+    def _view(self, arena, p):
+        o = self._offsets[id(p)]
+        return arena[o:o + p.numel()].view(p.shape)
+
+    def _deliver_grads(self, gid, grad_out):
+        """backward() of one of the four losses: scale the group's precomputed gradients by grad_out and
+        make sure `.grad` of its parameters points at them."""
+        g = self._group_slice(gid, self._garena)
+        if self._unit_grad_output:
+            pass
+        else:
+            self.ops.rowscale(g.view(1, -1), grad_out.reshape(1).to(g.dtype), 1, 1.0)
+        for p in self._group_params[gid]:
+            if p.grad is None or p.grad.data_ptr() != self._view(self._garena, p).data_ptr():
+                p.grad = self._view(self._garena, p)
+
+    # set False if the caller backwards with a non-unit grad_output (e.g. GradScaler with amp=True)
+    _unit_grad_output = True
+
+    # ------------------------------------------------------------------ reference API
+    def init_optimizers(self, lr, lr_actor=None, lr_critic=None, eps=1e-5):
+        self._ensure_arena()
+        return (_FusedAdamW(self, "wm", lr, eps), _FusedAdamW(self, "probe", lr, eps),
+                _FusedAdamW(self, "actor", lr_actor or lr, eps), _FusedAdamW(self, "critic", lr_critic or lr, eps))
+
+    @torch.no_grad()
+    def grad_clip(self, grad_clip, grad_clip_ac=None):
+        """dreamer.py:73-87: per-group clip_grad_norm_, returns the pre-clip norms."""
+        self._ensure_arena()
+        if self._dp is not None:
+            self._dp.allreduce_grads(self)
+        ws = self._buf("clip", 8)
+        self.ops.fill(ws, 0.0)
+        out = {}
+        for i, (gid, key, mx) in enumerate((("wm", "grad_norm", grad_clip), ("probe", "grad_norm_probe", grad_clip),
+                                            ("actor", "grad_norm_actor", grad_clip_ac or grad_clip),
+                                            ("critic", "grad_norm_critic", grad_clip_ac or grad_clip))):
+            g = self._group_slice(gid, self._garena)
+            self.ops.sumsq(g, ws[i:i + 1])
+            self.ops.clip_scale(g, ws[i:i + 1], mx, ws[4 + i:5 + i])
+            out[key] = ws[4 + i]
+        return out
+
+    def init_state(self, batch_size):
+        dev = next(self.parameters()).device
+        return (torch.zeros((batch_size, self.d.D), device=dev), torch.zeros((batch_size, self.d.Z), device=dev))
+
+    def inference(self, obs, in_state):
+        raise NotImplementedError("Dreamer.inference (actor path, T=1) is row N2 of SURVEY.md §8(f): next")
+
+    # ------------------------------------------------------------------ workspace
+    def _buf(self, name, *shape, dtype=torch.float32, zero=False):
+        key = (name, shape, dtype)
+        t = self._ws.get(key)
+        if t is None:
+            dev = self._arena.device
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+            self._ws[key] = t
+        return t
+
+    # ------------------------------------------------------------------ weights
+    def _w(self, p):      # rounded shadow (tensor-core operand)
+        return self._view(self._sarena, p)
+
+    def _raw(self, p):    # fp32 master (biases, LayerNorm affine)
+        return self._view(self._arena, p)
+
+    def _g(self, p):
+        return self._view(self._garena, p)
+
+    def _w2d(self, p):
+        return self._w(p).view(p.shape[0], -1)
+
+    def _prepare_weights(self):
+        """Per optimizer step: tf32-round the whole arena into the shadow arena (one kernel) and build the
+        conv / deconv weights in GEMM layout: conv (Cout,Cin,kh,kw)->(Cout,(kh,kw,Cin)); deconv
+        (Cin,Cout,kh,kw)->((kh,kw,Cout),Cin)."""
+        if not self._weights_dirty:
+            return
+        ops = self.ops
+        ops.round_copy(self._arena, self._sarena, True)
+        enc = self.wm.encoder.encoder_image.model
+        self._encw = []
+        for li, idx in enumerate((0, 2, 4, 6)):
+            w = enc[idx].weight
+            if li == 0:
+                self._encw.append(self._w(w).view(w.shape[0], -1))          # (c,kh,kw) order == native
+            else:
+                co, ci, kh, kw = w.shape
+                sh = self._buf(f"encw{li}", co, kh, kw, ci)
+                ops.permute4(self._w(w), sh, (0, 2, 3, 1))
+                self._encw.append(sh.view(co, kh * kw * ci))
+        dec = self.wm.decoder.image.model
+        self._decw = []
+        for li, idx in enumerate((2, 4, 6, 8)):
+            w = dec[idx].weight
+            ci, co, kh, kw = w.shape
+            sh = self._buf(f"decw{li}", kh, kw, co, ci)
+            ops.permute4(self._w(w), sh, (2, 3, 1, 0))
+            self._decw.append(sh.view(kh * kw * co, ci))
+        self._weights_dirty = False
+
+    def _mlp_params(self, mlp):
+        seq = mlp.model
+        L = mlp.hidden_layers
+        return SimpleNamespace(L=L, lin=[seq[3 * l] for l in range(L)], ln=[seq[3 * l + 1] for l in range(L)],
+                               out=seq[3 * L], hid=mlp.hidden_dim, out_dim=mlp.out_dim, in_dim=mlp.in_dim)
+
+    # ------------------------------------------------------------------ MLP forward / backward
+    def _mlp_fwd(self, mp, x_in, out, tag, rows_total=None, row0=0, save=False):
+        """out[rows, out_dim] = MLP(x_in).  With save=True the per-layer pre-norm x, post-ELU y and LN
+        statistics are kept in workspace buffers `tag` (rows_total rows, this call fills [row0, row0+rows))."""
+        ops = self.ops
+        rows = x_in.shape[0]
+        RT = rows_total or rows
+        inp = x_in
+        for l in range(mp.L):
+            if save:
+                x = self._buf(f"{tag}.x{l}", RT, mp.hid)[row0:row0 + rows]
+                y = self._buf(f"{tag}.y{l}", RT, mp.hid)[row0:row0 + rows]
+                mean = self._buf(f"{tag}.m{l}", RT)[row0:row0 + rows]
+                rstd = self._buf(f"{tag}.r{l}", RT)[row0:row0 + rows]
+            else:
+                x = self._buf(f"mlp.sx", rows, mp.hid)
+                y = self._buf(f"mlp.sy{l % 2}", rows, mp.hid)
+                mean = self._buf("mlp.sm", rows)
+                rstd = self._buf("mlp.sr", rows)
+            ops.gemm(inp, self._w(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
+            ops.ln_elu_fwd(x, self._raw(mp.ln[l].weight), self._raw(mp.ln[l].bias), 1e-3, y, mean, rstd)
+            inp = y
+        ops.gemm(inp, self._w(mp.out.weight), out, bias=self._raw(mp.out.bias))
+        return out
+
+    def _mlp_bwd(self, mp, x_in, dout, tag, rows_total=None, din=None, din_accum=False):
+        """Accumulates parameter grads of the MLP; optionally (+)= the input gradient into din."""
+        ops = self.ops
+        rows = x_in.shape[0]
+        RT = rows_total or rows
+        sv = lambda n, l: self._buf(f"{tag}.{n}{l}", RT, mp.hid)[:rows]
+        st = lambda n, l: self._buf(f"{tag}.{n}{l}", RT)[:rows]
+        dy = self._buf("mlp.dy", rows, mp.hid)
+        dx = self._buf("mlp.dx", rows, mp.hid)
+        ylast = sv("y", mp.L - 1)
+        ops.gemm(dout, ylast, self._g(mp.out.weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dout, self._g(mp.out.bias))
+        ops.gemm(dout, self._w(mp.out.weight), dy, b_mn=True)
+        for l in reversed(range(mp.L)):
+            ops.ln_elu_bwd(dy, sv("x", l), sv("y", l), self._raw(mp.ln[l].weight), st("m", l), st("r", l), dx,
+                           self._g(mp.ln[l].weight), self._g(mp.ln[l].bias), self._g(mp.lin[l].bias))
+            inp = x_in if l == 0 else sv("y", l - 1)
+            ops.gemm(dx, inp, self._g(mp.lin[l].weight), a_mn=True, b_mn=True, accumulate=True)
+            if l > 0:
+                ops.gemm(dx, self._w(mp.lin[l].weight), dy, b_mn=True)
+            elif din is not None:
+                ops.gemm(dx, self._w(mp.lin[0].weight), din, b_mn=True, res=din if din_accum else None)
+
+    # ------------------------------------------------------------------ noise
+    def _draw_noise(self, T, BI, N, H):
+        """Exp(1) noise for the categorical samples in the reference's consumption order;
+        Gaussian noise for the tanh_normal actor."""
+        d, dev = self.d, self._arena.device
+        post = self._buf("noise.post", T, BI, d.Z).exponential_()
+        if self.conf.actor_dist == "onehot":
+            actor = self._buf("noise.actor", H, N, d.A).exponential_()
+        else:
+            actor = self._buf("noise.actor", H, N, d.A).normal_()
+        prior = self._buf("noise.prior", H, N, d.Z).exponential_()
+        return dict(post=post, actor=actor, prior=prior)
+
+    # ------------------------------------------------------------------ training step
+    def training_step(self, obs, in_state, iwae_samples=None, imag_horizon=None, do_open_loop=False,
+                      do_image_pred=False, do_dream_tensors=False, noise=None):
+        """dreamer.py:113-186.  `noise` (optional, tests): dict(post=(T,BI,Z) Exp(1), actor=(H,N,A),
+        prior=(H,N,Z) Exp(1)) replacing the internally drawn sampling noise."""
+        assert "action" in obs, "`action` required in observation"
+        assert "reward" in obs, "`reward` required in observation"
+        assert "reset" in obs, "`reset` required in observation"
+        assert "terminal" in obs, "`terminal` required in observation"
+        if do_open_loop or do_image_pred or do_dream_tensors:
+            raise NotImplementedError("evaluation/logging branches (do_open_loop, do_image_pred, do_dream_tensors) "
+                                      "are row N4 of SURVEY.md §8(f): next")
+        I = int(iwae_samples or self.iwae_samples)
+        H = int(imag_horizon or self.imag_horizon)
+        T, B = obs["action"].shape[:2]
+        self._ensure_arena()
+        want_grad = torch.is_grad_enabled()
+        with torch.no_grad():
+            self._prepare_weights()
+            N = T * B * I
+            if noise is None:
+                noise = self._draw_noise(T, B * I, N, H)
+            if want_grad:
+                self.ops.fill(self._garena, 0.0)
+            wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"])
+            if want_grad:
+                self._wm_backward(obs, T, B, I, H)
+            self._dream(T, B, I, H, noise["actor"], noise["prior"])
+            ac_out = self._actor_critic(T, B, I, H, want_grad)
+        loss_model, loss_probe = wm_out["loss_model"], self.probe_model.dummy.detach() ** 2
+        loss_actor, loss_critic = ac_out["loss_actor"], ac_out["loss_critic"]
+        if want_grad:
+            gp = self._group_params
+            loss_model = _AttachGrads.apply(loss_model, self, "wm", *gp["wm"])
+            loss_probe = _AttachGrads.apply(loss_probe, self, "probe", *gp["probe"])
+            loss_actor = _AttachGrads.apply(loss_actor, self, "actor", *gp["actor"])
+            loss_critic = _AttachGrads.apply(loss_critic, self, "critic", *gp["critic"])
+        metrics = dict(wm_out["metrics"]); metrics.update(ac_out["metrics"])
+        tensors = dict(wm_out["tensors"])
+        tensors.update(policy_value=ac_out["value"][0].reshape(T, B, I).mean(-1))
+        return (loss_model, loss_probe, loss_actor, loss_critic), wm_out["out_state"], metrics, tensors, {}
+
+    # ------------------------------------------------------------------ world model forward
+    def _wm_forward(self, obs, in_state, T, B, I, H, noise_post):
+        ops, d, conf = self.ops, self.d, self.conf
+        NB, BI = T * B, B * I
+        N = NB * I
+        cd, IC = d.cd, d.IC
+        b = self._buf
+        enc = self.wm.encoder.encoder_image.model
+        cell = self.wm.core.cell
+        gru = cell.gru.layers[0]
+
+        # ---- encoder (encoders.py:72-96): im2col -> tcgen05 GEMM (+bias+ELU) x4, NHWC activations
+        img = obs["image"].reshape(NB, IC, 64, 64)
+        geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
+        x4 = img.permute(0, 2, 3, 1)
+        for li, (hin, hout, ci, co) in enumerate(geo):
+            col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
+            ops.im2col(x4, 4, 1 if li == 0 else 0, col, round_out=True)
+            act = b(f"enc.a{li}", NB * hout * hout, co)
+            ops.gemm(col, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
+            x4 = act.view(NB, hout, hout, co)
+        embed = b("enc.embed", NB, d.E)
+        ops.permute4(b("enc.a3", NB * 4, 8 * cd).view(NB, 4, 8 * cd, 1), embed.view(NB, 8 * cd, 4, 1), (0, 2, 1, 3),
+                     round_out=True)                                           # (h,w,c) -> reference (c,h,w) flatten
+
+        # ---- RSSM posterior unroll (rssm.py:21-78, 125-153)
+        mask = b("rssm.mask", T, BI)
+        ops.reset_mask(obs["reset"], I, mask)
+        action = obs["action"].reshape(NB, d.A)
+        ea = b("rssm.ea", NB, d.Hd); ops.gemm(embed, self._w(cell.post_mlp_e.weight), ea)      # hoisted over T
+        aa = b("rssm.aa", NB, d.Hd); ops.gemm(action, self._w(cell.a_mlp.weight), aa)
+        hin, zin = b("rssm.hin", T, BI, d.D), b("rssm.zin", T, BI, d.Z)
+        ops.mask_rows(in_state[0], mask[0], hin[0]); ops.mask_rows(in_state[1], mask[0], zin[0])
+        x1, za = b("rssm.x1", T, BI, d.Hd), b("rssm.za", T, BI, d.Hd)
+        m1, r1 = b("rssm.m1", T, BI), b("rssm.r1", T, BI)
+        gi, gh = b("rssm.gi", T, BI, 3 * d.D), b("rssm.gh", T, BI, 3 * d.D)
+        gates = b("rssm.gates", T, BI, 4 * d.D)
+        y2, pin = b("rssm.y2", T, BI, d.Hd), b("rssm.pin", T, BI, d.Hd)
+        m2, r2 = b("rssm.m2", T, BI), b("rssm.r2", T, BI)
+        post = b("rssm.post", T, BI, d.Z)
+        idx = b("rssm.idx", T, BI, d.G, dtype=torch.int32)
+        feats = b("feats", H + 1, N, d.F)            # feats[0] = world-model features, feats[1:] = dream
+        feat = feats[0].view(T, BI, d.F)
+        W = self._w
+        for t in range(T):
+            last = t == T - 1
+            ops.gemm(zin[t], W(cell.z_mlp.weight), x1[t], bias=self._raw(cell.z_mlp.bias), res=aa[t * B:(t + 1) * B],
+                     r_div=I)
+            ops.ln_elu_fwd(x1[t], self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za[t], m1[t], r1[t])
+            ops.gemm(za[t], W(gru.weight_ih), gi[t], bias=self._raw(gru.bias_ih))
+            ops.gemm(hin[t], W(gru.weight_hh), gh[t], bias=self._raw(gru.bias_hh))
+            ops.gru_fwd(gi[t], gh[t], hin[t], feat[t, :, :d.D], None if last else hin[t + 1],
+                        None if last else mask[t + 1], gates[t])
+            ops.gemm(feat[t, :, :d.D], W(cell.post_mlp_h.weight), y2[t], bias=self._raw(cell.post_mlp_h.bias),
+                     res=ea[t * B:(t + 1) * B], r_div=I)
+            ops.ln_elu_fwd(y2[t], self._raw(cell.post_norm.weight), self._raw(cell.post_norm.bias), 1e-3, pin[t],
+                           m2[t], r2[t])
+            ops.gemm(pin[t], W(cell.post_mlp.weight), post[t], bias=self._raw(cell.post_mlp.bias))
+            ops.cat_sample(post[t], noise_post[t], d.G, d.C, feat[t, :, d.D:], None if last else zin[t + 1],
+                           None if last else mask[t + 1], idx[t])
+        featN = feats[0]                                   # (N, F)
+        hN = featN[:, :d.D]
+        # batched prior (rssm.py:186-193)
+        yp, ppin = b("rssm.yp", N, d.Hd), b("rssm.ppin", N, d.Hd)
+        m3, r3 = b("rssm.m3", N), b("rssm.r3", N)
+        prior = b("rssm.prior", N, d.Z)
+        ops.gemm(hN, W(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
+        ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, ppin, m3, r3)
+        ops.gemm(ppin, W(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
+        out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
+
+        # ---- image decoder (decoders.py:111-180): Linear, then deconv = GEMM + col2im gather (+bias+ELU)
+        dec = self.wm.decoder.image.model
+        x0 = b("dec.x0", N, 32 * cd)
+        ops.gemm(featN, W(dec[0].weight), x0, bias=self._raw(dec[0].bias), round_out=True)
+        dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
+        xin = x0
+        for li, (hi, ho, k, ci, co) in enumerate(dgeo):
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co)
+            ops.gemm(xin, self._decw[li], cols)
+            bias = self._raw(dec[2 + 2 * li].bias)
+            if li < 3:
+                a = b(f"dec.d{li}", N, ho, ho, co)
+                ops.col2im(cols, hi, hi, k, bias, ACT_ELU, a, round_out=True)
+                xin = a.view(N * ho * ho, co)
+            else:
+                image_dec, diff = b("dec.image", N, IC, 64, 64), b("dec.diff", N, IC, 64, 64)
+                l_img, csum = b("loss.img", N), b("dec.csum", N, IC)
+                ops.col2im_imgloss(cols, N, hi, hi, IC, k, bias, img, I, image_dec, diff, l_img, csum)
+
+        # ---- reward / terminal heads (decoders.py:257-319)
+        rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)
+        yr, yt = b("head.yr", N, 1), b("head.yt", N, 1)
+        self._mlp_fwd(rp, featN, yr, "rew", save=True)
+        self._mlp_fwd(tp, featN, yt, "term", save=True)
+        l_rew, dyr, rec_r = b("loss.rew", N), b("head.dyr", N, 1), b("head.rec_r", N)
+        l_term, dyt, rec_t = b("loss.term", N), b("head.dyt", N, 1), b("head.rec_t", N)
+        ops.scalar_head_loss(0, yr, obs["reward"].reshape(NB), I, l_rew, dyr, rec_r)
+        ops.scalar_head_loss(1, yt, obs["terminal"].reshape(NB), I, l_term, dyt, rec_t)
+
+        # ---- KL + loss assembly (dreamer.py:328-379)
+        l_kl, kl_exact = b("loss.kl", N), b("loss.klx", N)
+        ent_post, ent_prior = b("loss.entq", N), b("loss.entp", N)
+        dpost_u, dprior = b("kl.dpost", N, d.Z), b("kl.dprior", N, d.Z)
+        kb = conf.kl_balance
+        ops.kl(post.view(N, d.Z), prior, idx.view(N, d.G), 0 if I == 1 else 1, -1.0 if kb == 0.5 else kb, d.G, d.C,
+               l_kl, kl_exact, ent_post, ent_prior, dpost_u, dprior)
+        w, tb = b("loss.w", N), b("loss.tb", NB, 8)
+        ops.wm_loss(NB, I, conf.kl_weight, conf.image_weight, conf.reward_weight, conf.terminal_weight, l_img, l_rew,
+                    l_term, l_kl, kl_exact, ent_prior, ent_post, w, tb)
+        means = b("loss.means", 8)
+        ops.colmean(tb, means)
+        tbv = tb.view(T, B, 8)
+        metrics = dict(loss_image=means[1], loss_reward=means[2], loss_terminal=means[3], loss_model=means[0],
+                       loss_kl=means[4], entropy_prior=means[5], entropy_post=means[6])
+        sel = (lambda x: x.view(T, B, I, *x.shape[1:])[:, :, 0]) if I == 1 else \
+              (lambda x: x.view(T, B, I, *x.shape[1:]).mean(2))
+        tensors = dict(loss_image=tbv[..., 1], image_rec=sel(image_dec), loss_reward=tbv[..., 2],
+                       reward_rec=sel(rec_r), loss_terminal=tbv[..., 3], terminal_rec=sel(rec_t),
+                       loss_kl=tbv[..., 4], entropy_prior=tbv[..., 5], entropy_post=tbv[..., 6])
+        return dict(loss_model=means[0], out_state=out_state, metrics=metrics, tensors=tensors)
+
+    # ------------------------------------------------------------------ world model backward
+    def _wm_backward(self, obs, T, B, I, H):
+        ops, d, conf = self.ops, self.d, self.conf
+        NB, BI = T * B, B * I
+        N = NB * I
+        cd, IC = d.cd, d.IC
+        b, W, G = self._buf, self._w, self._g
+        cell = self.wm.core.cell
+        gru = cell.gru.layers[0]
+        enc = self.wm.encoder.encoder_image.model
+        dec = self.wm.decoder.image.model
+        featN = b("feats", H + 1, N, d.F)[0]
+        w = b("loss.w", N)
+        dfeat = b("bwd.dfeat", N, d.F)
+
+        # ---- image decoder backward: seeds = w[n] * image_weight * (dec - target)
+        diff = b("dec.diff", N, IC, 64, 64)
+        csum = b("dec.csum", N, IC)
+        ops.rowscale(diff.view(N, IC * 4096), w, 1, conf.image_weight)
+        ops.rowscale(csum, w, 1, conf.image_weight)
+        ops.colsum(csum, G(dec[8].bias))
+        dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
+        gdec = [b(f"bwd.gdecw{li}", *self._decw[li].shape) for li in range(4)]
+        for g_ in gdec:
+            ops.fill(g_, 0.0)
+        dout4 = diff.permute(0, 2, 3, 1)                       # [n,y,x,c] view of the NCHW diff
+        for li in (3, 2, 1, 0):
+            hi, ho, k, ci, co = dgeo[li]
+            xin = b("dec.x0", N, 32 * cd) if li == 0 else b(f"dec.d{li - 1}", N, hi, hi, ci).view(N * hi * hi, ci)
+            if li == 0:
+                dcols = dout4.reshape(N, k * k * co)           # 5x5 input of a 5x5 kernel: im2col is the identity
+            else:
+                dcols = b(f"bwd.dcols{li}", N * hi * hi, k * k * co)
+                ops.im2col(dout4, k, 0, dcols, round_out=True)
+            ops.gemm(dcols, xin, gdec[li], a_mn=True, b_mn=True, accumulate=True)
+            dxin = b(f"bwd.dd{li}", N * hi * hi, ci)
+            ops.gemm(dcols, self._decw[li], dxin, b_mn=True, round_out=(li == 0))
+            if li > 0:
+                ops.bias_act_bwd(dxin, xin, ACT_ELU, G(dec[2 * li].bias))       # bias of the previous deconv
+                dout4 = dxin.view(N, hi, hi, ci)
+            else:
+                dx0 = dxin
+        for li, idx_ in enumerate((2, 4, 6, 8)):              # back to ConvTranspose2d layout (Cin,Cout,kh,kw)
+            wt = dec[idx_].weight
+            ci, co, kh, kw = wt.shape
+            ops.permute4(gdec[li].view(kh, kw, co, ci), G(wt), (3, 2, 0, 1))
+        ops.gemm(dx0, featN, G(dec[0].weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dx0, G(dec[0].bias))
+        ops.gemm(dx0, W(dec[0].weight), dfeat, b_mn=True)                      # first writer of dfeat
+
+        # ---- reward / terminal heads
+        rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)
+        dyr, dyt = b("head.dyr", N, 1), b("head.dyt", N, 1)
+        ops.rowscale(dyr, w, 1, conf.reward_weight)
+        ops.rowscale(dyt, w, 1, conf.terminal_weight)
+        self._mlp_bwd(rp, featN, dyr, "rew", din=dfeat, din_accum=True)
+        self._mlp_bwd(tp, featN, dyt, "term", din=dfeat, din_accum=True)
+
+        # ---- prior branch (batch_prior): dprior = kl_weight * w[n] * dKL/dprior
+        dprior = b("kl.dprior", N, d.Z)
+        ops.rowscale(dprior, w, 1, conf.kl_weight)
+        ppin, yp = b("rssm.ppin", N, d.Hd), b("rssm.yp", N, d.Hd)
+        dpp, dyp = b("bwd.dpp", N, d.Hd), b("bwd.dyp", N, d.Hd)
+        ops.gemm(dprior, ppin, G(cell.prior_mlp.weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dprior, G(cell.prior_mlp.bias))
+        ops.gemm(dprior, W(cell.prior_mlp.weight), dpp, b_mn=True)
+        ops.ln_elu_bwd(dpp, yp, ppin, self._raw(cell.prior_norm.weight), b("rssm.m3", N), b("rssm.r3", N), dyp,
+                       G(cell.prior_norm.weight), G(cell.prior_norm.bias), G(cell.prior_mlp_h.bias))
+        ops.gemm(dyp, featN[:, :d.D], G(cell.prior_mlp_h.weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(dyp, W(cell.prior_mlp_h.weight), dfeat[:, :d.D], b_mn=True, res=dfeat[:, :d.D])
+
+        # ---- BPTT through the posterior unroll
+        dfeat3 = dfeat.view(T, BI, d.F)
+        mask = b("rssm.mask", T, BI)
+        post, pin, y2 = b("rssm.post", T, BI, d.Z), b("rssm.pin", T, BI, d.Hd), b("rssm.y2", T, BI, d.Hd)
+        m2, r2 = b("rssm.m2", T, BI), b("rssm.r2", T, BI)
+        x1, za = b("rssm.x1", T, BI, d.Hd), b("rssm.za", T, BI, d.Hd)
+        m1, r1 = b("rssm.m1", T, BI), b("rssm.r1", T, BI)
+        gates, hin, zin = b("rssm.gates", T, BI, 4 * d.D), b("rssm.hin", T, BI, d.D), b("rssm.zin", T, BI, d.Z)
+        dpost_u = b("kl.dpost", N, d.Z).view(T, BI, d.Z)
+        w3 = w.view(T, BI)
+        dpost = b("bwd.dpost", T, BI, d.Z)
+        dy2, dx1 = b("bwd.dy2", T, BI, d.Hd), b("bwd.dx1", T, BI, d.Hd)
+        dgi, dgh = b("bwd.dgi", T, BI, 3 * d.D), b("bwd.dgh", T, BI, 3 * d.D)
+        dpin, dza = b("bwd.dpin", BI, d.Hd), b("bwd.dza", BI, d.Hd)
+        dhp, dhc = b("bwd.dhp", BI, d.D), b("bwd.dhc", BI, d.D)
+        dhin, dzin = b("bwd.dhin", BI, d.D), b("bwd.dzin", BI, d.Z)
+        for t in reversed(range(T)):
+            nxt = t < T - 1
+            ops.cat_st_bwd(post[t], d.G, d.C, dfeat3[t, :, d.D:], dzin if nxt else None, mask[t + 1] if nxt else None,
+                           dpost_u[t], w3[t], conf.kl_weight, dpost[t])
+            ops.gemm(dpost[t], W(cell.post_mlp.weight), dpin, b_mn=True)
+            ops.ln_elu_bwd(dpin, y2[t], pin[t], self._raw(cell.post_norm.weight), m2[t], r2[t], dy2[t],
+                           G(cell.post_norm.weight), G(cell.post_norm.bias), G(cell.post_mlp_h.bias))
+            ops.gemm(dy2[t], W(cell.post_mlp_h.weight), dhp, b_mn=True, res=dfeat3[t, :, :d.D])
+            ops.gru_bwd(dhp, dhin if nxt else None, mask[t + 1] if nxt else None, gates[t], hin[t], dgi[t], dgh[t], dhc)
+            ops.gemm(dgh[t], W(gru.weight_hh), dhin, b_mn=True, res=dhc)
+            ops.gemm(dgi[t], W(gru.weight_ih), dza, b_mn=True)
+            ops.ln_elu_bwd(dza, x1[t], za[t], self._raw(cell.in_norm.weight), m1[t], r1[t], dx1[t],
+                           G(cell.in_norm.weight), G(cell.in_norm.bias), G(cell.z_mlp.bias))
+            ops.gemm(dx1[t], W(cell.z_mlp.weight), dzin, b_mn=True)
+        # batched weight gradients over all T*BI rows
+        f2 = lambda x: x.view(N, x.shape[-1])
+        ops.gemm(f2(dpost), f2(pin), G(cell.post_mlp.weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(f2(dpost), G(cell.post_mlp.bias))
+        ops.gemm(f2(dy2), featN[:, :d.D], G(cell.post_mlp_h.weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(f2(dgh), f2(hin), G(gru.weight_hh), a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(f2(dgh), G(gru.bias_hh))
+        ops.gemm(f2(dgi), f2(za), G(gru.weight_ih), a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(f2(dgi), G(gru.bias_ih))
+        ops.gemm(f2(dx1), f2(zin), G(cell.z_mlp.weight), a_mn=True, b_mn=True, accumulate=True)
+        if I == 1:
+            dea, daa = f2(dy2), f2(dx1)
+        else:
+            dea, daa = b("bwd.dea", NB, d.Hd), b("bwd.daa", NB, d.Hd)
+            ops.group_sum(f2(dy2), I, dea); ops.group_sum(f2(dx1), I, daa)
+        embed = b("enc.embed", NB, d.E)
+        ops.gemm(dea, embed, G(cell.post_mlp_e.weight), a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(daa, obs["action"].reshape(NB, d.A), G(cell.a_mlp.weight), a_mn=True, b_mn=True, accumulate=True)
+        dembed = b("bwd.dembed", NB, d.E)
+        ops.gemm(dea, W(cell.post_mlp_e.weight), dembed, b_mn=True)
+
+        # ---- encoder backward
+        geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
+        da = b("bwd.da3", NB * 4, 8 * cd)
+        ops.permute4(dembed.view(NB, 8 * cd, 4, 1), da.view(NB, 4, 8 * cd, 1), (0, 2, 1, 3))
+        for li in (3, 2, 1, 0):
+            hin_, hout, ci, co = geo[li]
+            act = b(f"enc.a{li}", NB * hout * hout, co)
+            col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
+            ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
+            if li == 0:
+                ops.gemm(da, col, G(enc[0].weight).view(co, 16 * ci), a_mn=True, b_mn=True, accumulate=True)
+            else:
+                gw = b(f"bwd.gencw{li}", co, 16 * ci)
+                ops.fill(gw, 0.0)
+                ops.gemm(da, col, gw, a_mn=True, b_mn=True, accumulate=True)
+                ops.permute4(gw.view(co, 4, 4, ci), G(enc[2 * li].weight), (0, 3, 1, 2))
+                dcol = b(f"bwd.dcol{li}", NB * hout * hout, 16 * ci)
+                ops.gemm(da, self._encw[li], dcol, b_mn=True)
+                da_prev = b(f"bwd.da{li - 1}", NB * hin_ * hin_, ci)
+                ops.col2im(dcol, hout, hout, 4, None, ACT_NONE, da_prev.view(NB, hin_, hin_, ci), round_out=False)
+                da = da_prev
+
+    # ------------------------------------------------------------------ imagination rollout
+    def _dream(self, T, B, I, H, noise_actor, noise_prior):
+        """dreamer.py:188-216: H x { actor -> sample action -> forward_prior }, forward only (reinforce)."""
+        ops, d, conf = self.ops, self.d, self.conf
+        N = T * B * I
+        b, W = self._buf, self._w
+        cell = self.wm.core.cell
+        gru = cell.gru.layers[0]
+        feats = b("feats", H + 1, N, d.F)
+        ap = self._mlp_params(self.ac.actor)
+        alog = b("dream.alog", H, N, d.Aout)
+        actions = b("dream.actions", H, N, d.A)
+        aa, x, za = b("dream.aa", N, d.Hd), b("dream.x", N, d.Hd), b("dream.za", N, d.Hd)
+        mm, rr = b("dream.m", N), b("dream.r", N)
+        gi, gh = b("dream.gi", N, 3 * d.D), b("dream.gh", N, 3 * d.D)
+        yp, pp, prior = b("dream.yp", N, d.Hd), b("dream.pp", N, d.Hd), b("dream.prior", N, d.Z)
+        for i in range(H):
+            f = feats[i]
+            self._mlp_fwd(ap, f, alog[i], "actor", rows_total=H * N, row0=i * N, save=True)
+            if conf.actor_dist == "onehot":
+                ops.cat_sample(alog[i], noise_actor[i], 1, d.A, actions[i])
+            else:
+                ops.tanh_normal_sample(alog[i], noise_actor[i], actions[i])
+            ops.gemm(actions[i], W(cell.a_mlp.weight), aa)
+            ops.gemm(f[:, d.D:], W(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
+            ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr)
+            ops.gemm(za, W(gru.weight_ih), gi, bias=self._raw(gru.bias_ih))
+            ops.gemm(f[:, :d.D], W(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+            fn = feats[i + 1]
+            ops.gru_fwd(gi, gh, f[:, :d.D], fn[:, :d.D])
+            ops.gemm(fn[:, :d.D], W(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
+            ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pp, mm, rr)
+            ops.gemm(pp, W(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
+            ops.cat_sample(prior, noise_prior[i], d.G, d.C, fn[:, d.D:])
+
+    # ------------------------------------------------------------------ actor critic
+    def _actor_critic(self, T, B, I, H, want_grad):
+        """a2c.py:61-149 on the dreamed features (all inputs detached, dreamer.py:153-157)."""
+        ops, d, conf, ac = self.ops, self.d, self.conf, self.ac
+        N = T * B * I
+        J = H + 1
+        b = self._buf
+        if want_grad:                                   # log_only=False path: target sync + counter (a2c.py:76-79)
+            if ac.train_steps % conf.target_interval == 0:
+                self._group_slice("target", self._arena).copy_(self._group_slice("critic", self._arena))
+                self._group_slice("target", self._sarena).copy_(self._group_slice("critic", self._sarena))
+            ac.train_steps += 1
+        feats = b("feats", J, N, d.F)
+        fall = feats.view(J * N, d.F)
+        rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)
+        cp, ctp, ap = self._mlp_params(ac.critic), self._mlp_params(ac.critic_target), self._mlp_params(ac.actor)
+        rew, tlog = b("ac.rew", J * N, 1), b("ac.tlog", J * N, 1)
+        vt, v = b("ac.vt", J * N, 1), b("ac.v", J * N, 1)
+        self._mlp_fwd(rp, fall, rew, "scratch")
+        self._mlp_fwd(tp, fall, tlog, "scratch")
+        self._mlp_fwd(ctp, fall, vt, "scratch")
+        self._mlp_fwd(cp, fall, v, "critic", save=True)
+        term = b("ac.term", J, N)
+        adv, agae, target = b("ac.adv", H, N), b("ac.agae", H, N), b("ac.target", H, N)
+        weight, dv = b("ac.weight", H, N), b("ac.dv", H * N, 1)
+        sums = b("ac.sums", 8, dtype=torch.float64)
+        ops.fill(sums.view(torch.float32), 0.0)
+        ops.gae_critic(H, N, conf.gamma, conf.lambda_gae, vt, v, rew, tlog, term, adv, agae, target, weight, dv, sums)
+        alog = b("dream.alog", H, N, d.Aout).view(H * N, d.Aout)
+        actions = b("dream.actions", H, N, d.A).view(H * N, d.A)
+        dal = b("ac.dalog", H * N, d.Aout)
+        if conf.actor_dist == "onehot":
+            ops.actor_loss_onehot(conf.entropy, alog, actions, agae, weight, dal, sums[5:7])
+        else:
+            ops.actor_loss_tanh_normal(conf.entropy, alog, actions, agae, weight, dal, sums[5:7])
+        if want_grad:
+            fH = fall[:H * N]
+            self._mlp_bwd(cp, fH, dv, "critic", rows_total=J * N)
+            self._mlp_bwd(ap, fH, dal, "actor", rows_total=H * N)
+        hm = float(H * N)
+        s = sums
+        r_mean = s[3] / hm
+        r_var = torch.clamp((s[4] - s[3] * s[3] / hm) / (hm - 1.0), min=0.0)
+        f32 = lambda x: x.to(torch.float32)
+        metrics = dict(loss_critic=f32(s[0] / hm), loss_actor=f32(s[5] / hm), policy_entropy=f32(s[6] / hm),
+                       policy_value=f32(s[1] / float(N)), policy_value_im=f32(s[2] / hm), policy_reward=f32(r_mean),
+                       policy_reward_std=f32(r_var.sqrt()))
+        return dict(loss_actor=metrics["loss_actor"], loss_critic=metrics["loss_critic"], metrics=metrics,
+                    value=v.view(J, N), tensors=dict(value=v.view(J, N), value_target=target, value_advantage=adv,
+                                                     value_advantage_gae=agae, value_weight=weight))
+
+    def __str__(self):
+        n = sum(p.numel() for p in self.parameters())
+        return f"Model: {n} parameters (pydreamer_b200: sm_100a kernels behind the pydreamer Dreamer API)"

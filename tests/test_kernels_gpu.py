@@ -126,11 +126,16 @@ def test_gemm_tf32_error_on_random_operands(ops, native_ops):
 
 def test_gemm_skinny_shapes_fall_to_simt(ops, ref):
     ops.set_gemm_impl(0)
-    for (M, N, K) in [(2500, 1, 400), (2500, 18, 400), (777, 1000, 18)]:
+    for (M, N, K) in [(2500, 1, 400), (2500, 6, 400), (777, 1000, 18), (333, 1000, 6)]:
         A, B = rnd(M, K, seed=1), rnd(N, K, seed=2)
         C, Cr = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
         ops.gemm(A, B, C); ref.gemm(A, B, Cr)
         close(C, Cr, rtol=1e-5, what=f"skinny {M}x{N}x{K}")
+    # N = 18 (actor logits) is wide enough for the tensor-core path: TF32 operand precision
+    A, B = rnd(2500, 400, seed=1), rnd(18, 400, seed=2)
+    C, Cr = torch.empty(2500, 18, device=DEV), torch.empty(2500, 18, device=DEV)
+    ops.gemm(A, B, C); ref.gemm(A, B, Cr)
+    close(C, Cr, rtol=2e-3, what="N=18 tf32")
 
 
 @pytest.mark.parametrize("M,N", [(50, 1000), (2500, 400), (7, 1000), (1000, 33)])
