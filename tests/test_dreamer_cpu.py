@@ -1,0 +1,112 @@
+"""Host-side composition + hand-written backward of pydreamer_b200.Dreamer, checked on CPU.
+
+The module is run on the reference op table (oracle/ref_ops.py, plain torch) instead of the CUDA kernels, so
+this isolates the schedule written in pydreamer_b200/dreamer.py (what feeds what, the manual BPTT, gradient
+routing to the four optimizers) from the kernels themselves (tests/test_kernels_gpu.py).  Expected values are
+the committed outputs of the unmodified reference (tests/golden).  Tolerance: 2e-4 relative."""
+import pytest
+import torch
+
+from oracle.ref_ops import RefOps
+from pydreamer_b200 import ops as pd_ops
+from pydreamer_b200.dreamer import Dreamer
+from tests.util import CASES, build_case, seeded_weights
+
+
+@pytest.fixture()
+def ref_ops():
+    pd_ops.set_ops_for_testing(RefOps("cpu"))
+    yield
+    pd_ops.set_ops_for_testing(None)
+
+
+def run_model(case):
+    fx, conf, obs, state, noise = build_case(case)
+    model = Dreamer(conf)
+    model.load_state_dict(seeded_weights(model.state_dict(), fx))
+    opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
+    losses, out_state, metrics, tensors, dream = model.training_step(obs, state, noise=noise)
+    for o in opts:
+        o.zero_grad()
+    for l in losses:
+        l.backward()
+    return fx, conf, model, opts, losses, out_state, metrics, tensors
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_training_step_matches_reference_golden(ref_ops, case):
+    fx, conf, model, opts, losses, out_state, metrics, tensors = run_model(case)
+    assert [tuple(l.shape) for l in losses] == [(), (1,), (), ()]
+    for got, want in zip(losses, fx["losses"]):
+        assert abs(float(got.detach().reshape(-1)[0]) - want) <= 2e-5 * max(1.0, abs(want))
+    assert set(metrics) == set(fx["metrics"])
+    for k, want in fx["metrics"].items():
+        assert abs(float(metrics[k]) - want) <= 2e-4 * max(1.0, abs(want)), k
+    assert set(tensors) == set(fx["tensor_sums"])
+    for k, want in fx["tensor_abs_sums"].items():
+        got = float(tensors[k].double().abs().sum())
+        assert abs(got - want) <= 2e-4 * max(want, 1e-6), (k, got, want)
+    named = dict(model.named_parameters())
+    assert {k for k, p in named.items() if p.requires_grad} == set(fx["grad_norms"])
+    worst = ("", 0.0)
+    for k, want in fx["grad_norms"].items():
+        g = named[k].grad
+        assert g is not None, k
+        got = float(g.double().norm())
+        err = abs(got - want) / max(want, 1e-6)
+        if err > worst[1]:
+            worst = (k, err)
+        assert abs(got - want) <= 2e-4 * max(want, 1e-6) + 1e-9, (k, got, want)
+        assert abs(float(g.double().sum()) - fx["grad_sums"][k]) <= 5e-4 * max(want, 1e-6) * g.numel() ** 0.5 + 1e-8, k
+    assert not out_state[0].requires_grad and abs(float(out_state[0].double().sum()) - fx["out_state_h_sum"]) < 1e-3
+    assert all(p.grad is None for p in model.ac.critic_target.parameters())
+
+
+def test_state_dict_roundtrip_and_grad_clip_and_optimizer(ref_ops):
+    fx, conf, model, opts, losses, out_state, metrics, tensors = run_model("tiny_onehot")
+    sd = model.state_dict()
+    assert "wm.core.cell.gru.layers.0.weight_hh" in sd and "ac.critic_target.model.12.bias" in sd
+    assert "probe_model.dummy" in sd and "wm.decoder.image.model.8.weight" in sd
+    # torch reference for clip + AdamW on a copy of params/grads
+    named = dict(model.named_parameters())
+    groups = dict(wm=list(model.wm.parameters()), actor=list(model.ac.actor.parameters()),
+                  critic=list(model.ac.critic.parameters()))
+    clones = {g: [torch.nn.Parameter(p.detach().clone()) for p in ps] for g, ps in groups.items()}
+    for g, ps in groups.items():
+        for c, p in zip(clones[g], ps):
+            c.grad = p.grad.detach().clone()
+    norms = model.grad_clip(0.5, 0.01)           # tiny thresholds so that clipping is active
+    assert set(norms) == {"grad_norm", "grad_norm_probe", "grad_norm_actor", "grad_norm_critic"}
+    tn = {g: torch.nn.utils.clip_grad_norm_(clones[g], 0.5 if g == "wm" else 0.01) for g in clones}
+    assert abs(float(norms["grad_norm"]) - float(tn["wm"])) <= 1e-4 * float(tn["wm"])
+    assert abs(float(norms["grad_norm_actor"]) - float(tn["actor"])) <= 1e-4 * float(tn["actor"])
+    topts = dict(wm=torch.optim.AdamW(clones["wm"], lr=conf.adam_lr, eps=conf.adam_eps),
+                 actor=torch.optim.AdamW(clones["actor"], lr=conf.adam_lr_actor, eps=conf.adam_eps),
+                 critic=torch.optim.AdamW(clones["critic"], lr=conf.adam_lr_critic, eps=conf.adam_eps))
+    for o in opts:
+        o.step()
+    for o in topts.values():
+        o.step()
+    for g, ps in groups.items():
+        for c, p in zip(clones[g], ps):
+            assert torch.allclose(c.detach(), p.detach(), rtol=1e-5, atol=1e-7), g
+    # second step reuses the workspace, carries state, target critic no longer synced
+    fx2, conf2, obs, state, noise = build_case("tiny_onehot")
+    losses2, out_state2, *_ = model.training_step(obs, out_state, noise=noise)
+    assert all(torch.isfinite(l).all() for l in losses2)
+    assert model.ac.train_steps == 2
+
+
+def test_no_grad_mode_skips_backward_and_unsupported_configs_raise(ref_ops):
+    fx, conf, obs, state, noise = build_case("tiny_onehot")
+    model = Dreamer(conf)
+    with torch.no_grad():
+        losses, *_ = model.training_step(obs, state, noise=noise)
+    assert not losses[0].requires_grad and model.ac.train_steps == 0
+    from pydreamer_b200.config import make_conf
+    for bad in (dict(gru_type="gru_layernorm"), dict(image_encoder="dense"), dict(actor_grad="dynamics"),
+                dict(probe_model="map"), dict(stoch_discrete=0)):
+        with pytest.raises(NotImplementedError):
+            Dreamer(make_conf("tiny", **bad))
+    with pytest.raises(NotImplementedError):
+        model.training_step(obs, state, do_image_pred=True)
