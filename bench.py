@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — gradient-steps/sec (and imagined-samples/sec) of the Dreamer training step on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (hand-written sm_100a kernels)
+  python bench.py --impl reference --gpus N ...            # the reference's own CPU path (rank 0 only)
+
+One "step" = Dreamer.training_step + 4x backward + grad_clip(200,200) + 4x AdamW on one synthetic replay batch
+(BASELINE.json configs[1]: Atari shape, deter 2048, stoch 32x32, batch 50 x seq 50, imag_horizon 15, 64x64x3) —
+the reference's own `train/fps` (train.py:243-246) minus data loading.  Prints ONE JSON line (rank 0).
+
+  value : steps/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the public module API with the batch copied from pinned host memory every step and
+          the four losses read back to the host inside the timed region
+  roofline : the dominant kernel (pd_gemm_tf32_kernel: tcgen05 TF32 GEMM) — algorithmic FLOPs of every launch in
+          one step / their CUDA-event durations, against MEASURED_PEAKS.json
+  cpu_baseline : the reference implementation on this box's host cores (rank 0, N=1), bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# FLOPs of one gradient step at the Atari shape, counted with torch.utils.flop_counter on the reference
+# (SURVEY.md §8a row a17): 3113.3 G forward + 1519.7 G backward.
+ALGO_FLOPS_ATARI = 4.633e12
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="atari")
+    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", help="device of the --impl reference arm (cpu per the contract)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="sequences per reference sample step (0 = auto)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_module():
+    """(Dreamer class, kind): the unmodified reference installed under baseline/_ref if present (it is git-ignored but
+    travels with gpurun), else the oracle port."""
+    ref_path = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_path, "pydreamer")):
+        sys.path.insert(0, ref_path)
+        try:
+            from pydreamer.models import Dreamer as RefDreamer  # the reference's own module
+
+            return RefDreamer, "reference"
+        except Exception:
+            pass
+    return None, "port"
+
+
+def time_reference(conf, device, B, steps, warmup):
+    """Seconds per gradient step of the reference path at batch B (its own Dreamer if installed, else the oracle)."""
+    from pydreamer_b200.replay import synthetic_batch
+
+    torch.distributions.Distribution.set_default_validate_args(False)       # train.py:30
+    RefDreamer, kind = reference_module()
+    obs = synthetic_batch(conf, seed=1234, B=B, device=device)
+    times = []
+    if kind == "reference":
+        if str(device) != "cpu":
+            torch.backends.cudnn.benchmark = True                            # train.py:31
+        model = RefDreamer(conf).to(device)
+        opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
+        state = model.init_state(B * conf.iwae_samples)
+        for it in range(warmup + steps):
+            if str(device) != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            losses, state, *_ = model.training_step(obs, state)
+            for o in opts:
+                o.zero_grad()
+            for l in losses:
+                l.backward()
+            model.grad_clip(conf.grad_clip, conf.grad_clip_ac)
+            for o in opts:
+                o.step()
+            if str(device) != "cpu":
+                torch.cuda.synchronize()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        from oracle import dreamer_oracle as O
+        from pydreamer_b200.dreamer import Dreamer
+
+        sd = {k: v.to(device).requires_grad_(not k.startswith("ac.critic_target"))
+              for k, v in Dreamer(conf).state_dict().items()}
+        params = [v for v in sd.values() if v.requires_grad]
+        opt = torch.optim.AdamW(params, lr=conf.adam_lr, eps=conf.adam_eps)
+        state = (torch.zeros(B, conf.deter_dim, device=device), torch.zeros(B, conf.stoch_dim * conf.stoch_discrete, device=device))
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            noise = O.draw_noise(conf, conf.batch_length, B, device=device)
+            res = O.training_step(sd, conf, obs, state, noise)
+            opt.zero_grad()
+            for l in res["losses"]:
+                l.backward()
+            torch.nn.utils.clip_grad_norm_(params, conf.grad_clip)
+            opt.step()
+            state = res["out_state"]
+            if str(device) != "cpu":
+                torch.cuda.synchronize()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), kind
+
+
+def run_reference(args):
+    from pydreamer_b200.config import make_conf
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    conf = make_conf(args.config, device=args.ref_device)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    full_B = conf.batch_size
+    B = args.ref_batch or (max(1, full_B // 10) if args.ref_device == "cpu" else full_B)
+    sec, kind = time_reference(conf, args.ref_device, B, args.steps, args.warmup)
+    scale = full_B / B                      # the CPU path is throughput-bound: time is linear in sequences per batch
+    sps = 1.0 / (sec * scale)
+    T, I, H = conf.batch_length, conf.iwae_samples, conf.imag_horizon
+    sample = (f"{B} of {full_B} sequences x T={T}, H={H} per sample step on {args.ref_device}; "
+              f"steps/s = 1 / (sample seconds x {scale:g})")
+    line = dict(metric="grad_steps_per_sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 * sec * scale, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                imagined_samples_per_sec=sps * T * full_B * I * H,
+                config=dict(workload=f"{args.config}: Dreamer.training_step+backward+clip+AdamW, B={full_B} T={T} H={H} "
+                                     f"deter={conf.deter_dim} stoch={conf.stoch_dim}x{conf.stoch_discrete}",
+                            global_batch=full_B, seq_len=T),
+                cpu_baseline=dict(value=sps, unit="steps/s", cores=cores if args.ref_device == "cpu" else 0, kind=kind,
+                                  sample=sample),
+                e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from pydreamer_b200.config import make_conf
+    from pydreamer_b200.dreamer import Dreamer
+    from pydreamer_b200.replay import obs_bytes, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    conf = make_conf(args.config, device=str(dev))
+    T, B, I, H = conf.batch_length, conf.batch_size, conf.iwae_samples, conf.imag_horizon
+    model = Dreamer(conf).to(dev)
+    model._ensure_arena()
+    if args.gemm == "simt":
+        model.ops.set_gemm_impl(1)
+    if world > 1:
+        from pydreamer_b200.parallel import GradAllReduce
+
+        model._dp = GradAllReduce(world)
+        model._dp.broadcast_params(model)
+    opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
+    host = synthetic_batch(conf, seed=1234 + rank, pin=True)           # per-rank shard of the global batch (weak scaling)
+    dev_obs = {k: v.to(dev) for k, v in host.items()}
+    state = {"s": model.init_state(B * I)}
+    host_loss = torch.empty(4, pin_memory=True)
+
+    def step(obs):
+        losses, state["s"], metrics, tensors, _ = model.training_step(obs, state["s"])
+        for o in opts:
+            o.zero_grad()
+        for l in losses:
+            l.backward()
+        model.grad_clip(conf.grad_clip, conf.grad_clip_ac)
+        for o in opts:
+            o.step()
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_obs)
+    n0 = model.ops.launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(lambda: step(dev_obs), args.steps)
+    launches = (model.ops.launch_count() - n0) // args.steps
+    clocks = cs.summary()
+
+    def e2e_step():
+        obs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        losses = step(obs)
+        host_loss.copy_(torch.stack([l.detach().reshape(-1)[0] for l in losses]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the caller consumes the losses every step
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- roofline of the dominant kernel: every pd_gemm launch of one step, CUDA-event timed
+    model.ops.gemm_profile = []
+    step(dev_obs)
+    torch.cuda.synchronize()
+    prof, model.ops.gemm_profile = model.ops.gemm_profile, None
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
+    gemm_flops = sum(f for _, _, f, _ in prof)
+    pk = peaks()
+    steps_per_s = world * args.steps / (ms / 1000.0)
+    e2e_per_s = world * args.steps / (ms_e2e / 1000.0)
+    per_step_samples = T * B * I * H
+    achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    line = dict(
+        metric="grad_steps_per_sec", value=steps_per_s, unit="steps/s", n_gpus=world, steps=args.steps,
+        warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="tf32 (fp32 storage, fp32 accumulate)", data="synthetic",
+        imagined_samples_per_sec=steps_per_s * per_step_samples,
+        config=dict(workload=f"{args.config}: Dreamer.training_step+4x backward+grad_clip+4x AdamW, per-GPU B={B} T={T} H={H} "
+                             f"I={I} deter={conf.deter_dim} stoch={conf.stoch_dim}x{conf.stoch_discrete} image 64x64x3",
+                    global_batch=B * world, seq_len=T, parallelism=f"dp{world}",
+                    l2="per-step working set (~15 GB of activations) is far larger than the 126 MB L2; no flush needed"),
+        e2e=dict(value=e2e_per_s, unit="steps/s", h2d_bytes_per_step=obs_bytes(host), d2h_bytes_per_step=16,
+                 ms_per_step=ms_e2e / args.steps),
+        gpu_launches=int(launches) * args.steps,
+        launches_per_step=int(launches),
+        clocks=clocks,
+        roofline=dict(bound="tensor", kernel="pd_gemm_tf32_kernel (tcgen05.mma kind::tf32)", achieved=achieved,
+                      peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"],
+                      peak_source=pk["source"] + ": cuBLAS bf16 sustained; tf32 nominal peak is half of bf16",
+                      traffic=None, gemm_launches_per_step=len(prof), gemm_ms_per_step=gemm_ms,
+                      gemm_share_of_step=gemm_ms / (ms / args.steps), gemm_flops_per_step=gemm_flops,
+                      step_algorithmic_tflop=ALGO_FLOPS_ATARI / 1e12 if args.config == "atari" else None,
+                      step_tflops=(ALGO_FLOPS_ATARI / 1e12) / (ms / args.steps / 1000.0) if args.config == "atari" else None),
+    )
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cconf = make_conf(args.config, device="cpu")
+        Bs = max(1, B // 10)
+        sec, kind = time_reference(cconf, "cpu", Bs, 1, 1)
+        scale = B / Bs
+        line["cpu_baseline"] = dict(value=1.0 / (sec * scale), unit="steps/s", cores=cores, kind=kind,
+                                    sample=f"{Bs} of {B} sequences x T={T}, H={H}: 1 warm-up + 1 timed sample step "
+                                           f"({sec:.1f} s); steps/s = 1/(sample s x {scale:g})")
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -45,6 +45,7 @@ class NativeOps:
         if rc != 0:
             raise RuntimeError(f"pd_create failed ({rc}): device {idx} is not an sm_100 GPU or the driver is too old")
         self.h = h
+        self.gemm_profile = None   # list of (start_event, end_event, flops) when bench.py profiles a step
 
     def __del__(self):
         try:
@@ -78,10 +79,17 @@ class NativeOps:
         K = A.shape[0] if a_mn else A.shape[1]
         assert (A.shape[1] if a_mn else A.shape[0]) == M, (A.shape, C.shape, a_mn)
         assert (B.shape == (K, N)) if b_mn else (B.shape == (N, K)), (B.shape, (N, K), b_mn)
+        prof = self.gemm_profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = self.lib.pd_gemm(self.h, M, N, K, _ptr(A), _ld(A), int(a_mn), _ptr(B), _ld(B), int(b_mn),
                               _ptr(C), _ld(C), _ptr(bias), _ptr(res), _ld(res) if res is not None else 0,
                               int(r_div), int(act), int(round_out), int(accumulate), self._s())
         self._ck(rc, "pd_gemm")
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), int(accumulate))))
         return C
 
     # ------------------------------------------------------------------ rowwise
