@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", help="device of the --impl reference arm (cpu per the contract)")
     ap.add_argument("--ref-batch", type=int, default=0, help="sequences per reference sample step (0 = auto)")
+    ap.add_argument("--dump-gemm-profile", default="", help="write the per-shape GEMM timing table of one step here")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU reference (0 = calibrate)")
     return ap.parse_args()
 
 
@@ -120,6 +122,39 @@ def reference_module():
     return None, "port"
 
 
+def host_cores():
+    """Cores this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def pick_cpu_threads(conf, requested=0):
+    """The eager CPU path does not scale to arbitrarily many threads at these tensor sizes (and oversubscribing a
+    cgroup-limited box is catastrophic), so probe a few thread counts on a 1-sequence step and keep the fastest."""
+    if requested:
+        torch.set_num_threads(requested)
+        return requested
+    avail = host_cores()
+    cands = sorted({c for c in (avail, 64, 32, 16, 8) if c <= avail}, reverse=True) or [1]
+    best, best_t = cands[-1], float("inf")
+    for c in reversed(cands):                       # ascending
+        torch.set_num_threads(c)
+        t, _ = time_reference(conf, "cpu", 1, 1, 1)
+        if t < best_t * 0.95:
+            best, best_t = c, t
+        else:
+            break
+    torch.set_num_threads(best)
+    return best
+
+
 def time_reference(conf, device, B, steps, warmup):
     """Seconds per gradient step of the reference path at batch B (its own Dreamer if installed, else the oracle)."""
     from pydreamer_b200.replay import synthetic_batch
@@ -183,8 +218,7 @@ def run_reference(args):
     if rank != 0:
         return
     conf = make_conf(args.config, device=args.ref_device)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_cpu_threads(conf, args.cpu_threads) if args.ref_device == "cpu" else 0
     full_B = conf.batch_size
     B = args.ref_batch or (max(1, full_B // 10) if args.ref_device == "cpu" else full_B)
     sec, kind = time_reference(conf, args.ref_device, B, args.steps, args.warmup)
@@ -289,6 +323,14 @@ def run_ours(args):
     step(dev_obs)
     torch.cuda.synchronize()
     prof, model.ops.gemm_profile = model.ops.gemm_profile, None
+    if args.dump_gemm_profile and rank == 0:
+        agg = {}
+        for e0, e1, f, shp in prof:
+            a = agg.setdefault(shp, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
+        rows = sorted(([list(k), v[0], v[1], v[2], v[2] / max(v[1], 1e-9) / 1e9] for k, v in agg.items()), key=lambda r: -r[2])
+        with open(args.dump_gemm_profile, "w") as f:
+            json.dump(dict(columns=["(M,N,K,a_mn,b_mn,acc)", "launches", "ms", "flops", "TFLOP/s"], rows=rows), f, indent=0)
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     pk = peaks()
@@ -319,9 +361,8 @@ def run_ours(args):
                       step_tflops=(ALGO_FLOPS_ATARI / 1e12) / (ms / args.steps / 1000.0) if args.config == "atari" else None),
     )
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
         cconf = make_conf(args.config, device="cpu")
+        cores = pick_cpu_threads(cconf, args.cpu_threads)
         Bs = max(1, B // 10)
         sec, kind = time_reference(cconf, "cpu", Bs, 1, 1)
         scale = B / Bs

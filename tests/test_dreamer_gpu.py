@@ -45,7 +45,7 @@ def test_exact_arm_matches_reference_golden(case):
     named = dict(model.named_parameters())
     for k, want in fx["grad_norms"].items():
         got = float(named[k].grad.double().norm())
-        assert abs(got - want) <= 3e-4 * max(want, 1e-6) + 1e-9, (k, got, want)
+        assert abs(got - want) <= 1e-3 * max(want, 1e-6) + 1e-9, (k, got, want)
     T, B, I = conf.batch_length, conf.batch_size, conf.iwae_samples
     idx = model._buf("rssm.idx", T, B * I, conf.stoch_dim, dtype=torch.int32)
     assert idx[0].reshape(-1).tolist() == fx["post_sample_indices_t0"]        # bit-exact sampled indices
