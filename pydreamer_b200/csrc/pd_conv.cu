@@ -26,6 +26,61 @@ __global__ void im2col_kernel(long total, int Hout, int Wout, int Cc, int k, int
     }
 }
 
+// NHWC fast path: one thread moves 4 consecutive channels (16 B) of one tap.
+__global__ void im2col_v4_kernel(long total4, int Hout, int Wout, int C4, int k, const float* __restrict__ in,
+                                 long sN, long sY, long sX, float* __restrict__ col, long ldcol, int round_out) {
+    const int KK4 = k * k * C4;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        long row = idx / KK4;
+        int kidx = (int)(idx % KK4);
+        int c4 = kidx % C4;
+        int r = kidx / C4;
+        int kw = r % k, kh = r / k;
+        int ox = (int)(row % Wout);
+        long t = row / Wout;
+        int oy = (int)(t % Hout);
+        long n = t / Hout;
+        float4 v = *reinterpret_cast<const float4*>(in + n * sN + (long)(2 * oy + kh) * sY + (long)(2 * ox + kw) * sX + c4 * 4);
+        if (round_out) { v.x = pd_tf32(v.x); v.y = pd_tf32(v.y); v.z = pd_tf32(v.z); v.w = pd_tf32(v.w); }
+        *reinterpret_cast<float4*>(col + row * ldcol + (long)kidx * 4) = v;
+    }
+}
+
+__global__ void col2im_v4_kernel(long total4, int Hin, int Win, int Hout, int Wout, int C4, int k,
+                                 const float* __restrict__ col, long ldcol, const float* __restrict__ bias, int act,
+                                 int round_out, float* __restrict__ out, long sN, long sY, long sX) {
+    const int Cc = C4 * 4;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        int c4 = (int)(idx % C4);
+        long t = idx / C4;
+        int x = (int)(t % Wout);
+        t /= Wout;
+        int y = (int)(t % Hout);
+        long n = t / Hout;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = y & 1; kh < k; kh += 2) {
+            int iy = (y - kh) >> 1;
+            if (iy < 0) break;
+            if (iy >= Hin) continue;
+            for (int kw = x & 1; kw < k; kw += 2) {
+                int ix = (x - kw) >> 1;
+                if (ix < 0) break;
+                if (ix >= Win) continue;
+                const float4 v = *reinterpret_cast<const float4*>(col + ((n * Hin + iy) * Win + ix) * ldcol +
+                                                                   (long)(kh * k + kw) * Cc + c4 * 4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + c4 * 4);
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        if (act == PD_ACT_ELU) { acc.x = pd_elu(acc.x); acc.y = pd_elu(acc.y); acc.z = pd_elu(acc.z); acc.w = pd_elu(acc.w); }
+        if (round_out) { acc.x = pd_tf32(acc.x); acc.y = pd_tf32(acc.y); acc.z = pd_tf32(acc.z); acc.w = pd_tf32(acc.w); }
+        *reinterpret_cast<float4*>(out + n * sN + (long)y * sY + (long)x * sX + c4 * 4) = acc;
+    }
+}
+
 __device__ __forceinline__ float col2im_gather(const float* __restrict__ col, long ldcol, long n, int y, int x, int c,
                                                int Hin, int Win, int Cc, int k) {
     float acc = 0.f;
@@ -149,6 +204,14 @@ int pd_im2col(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, int korder,
     PD_REQUIRE(h, Hin >= k && Win >= k, "pd_im2col: input %dx%d smaller than kernel %d", Hin, Win, k);
     int Hout = (Hin - k) / 2 + 1, Wout = (Win - k) / 2 + 1;
     long total = (long)NB * Hout * Wout * k * k * Cc;
+    const bool v4 = korder == 0 && sC == 1 && (Cc % 4) == 0 && (sN % 4) == 0 && (sY % 4) == 0 && (sX % 4) == 0 &&
+                    (ldcol % 4) == 0 && ((((uintptr_t)in) | ((uintptr_t)col)) & 15) == 0;
+    if (v4) {
+        im2col_v4_kernel<<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+            total / 4, Hout, Wout, Cc / 4, k, in, sN, sY, sX, col, ldcol, round_out && h->round_ops);
+        PD_CHECK_LAUNCH(h, "im2col_v4");
+        return PD_OK;
+    }
     im2col_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         total, Hout, Wout, Cc, k, korder, in, sN, sY, sX, sC, col, ldcol, round_out && h->round_ops);
     PD_CHECK_LAUNCH(h, "im2col");
@@ -159,6 +222,14 @@ int pd_col2im(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc
               const float* bias, int act, int round_out, float* out, long sN, long sY, long sX, long sC,
               void* stream) {
     long total = (long)NB * Hout * Wout * Cc;
+    const bool v4 = sC == 1 && (Cc % 4) == 0 && (sN % 4) == 0 && (sY % 4) == 0 && (sX % 4) == 0 && (ldcol % 4) == 0 &&
+                    ((((uintptr_t)out) | ((uintptr_t)col)) & 15) == 0 && (!bias || (((uintptr_t)bias) & 15) == 0);
+    if (v4) {
+        col2im_v4_kernel<<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+            total / 4, Hin, Win, Hout, Wout, Cc / 4, k, col, ldcol, bias, act, round_out && h->round_ops, out, sN, sY, sX);
+        PD_CHECK_LAUNCH(h, "col2im_v4");
+        return PD_OK;
+    }
     col2im_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         total, Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, act, round_out && h->round_ops, out, sN, sY, sX, sC);
     PD_CHECK_LAUNCH(h, "col2im");

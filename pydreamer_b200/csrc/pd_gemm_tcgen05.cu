@@ -31,13 +31,15 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;   // 256 (power of two)
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGING = 4 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose buffers
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGING;
 
 struct GemmArgs {
     int M, N, K;
     int a_mn, b_mn;
     int num_m, num_n, splits, kb_total, kb_per_split;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
+    int extras_on_split0;      // split-K of a plain (non-accumulate) GEMM: split 0 adds bias/residual, C pre-zeroed
     PdEpilogue epi;
 };
 
@@ -229,48 +231,52 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // TMEM -> registers (thread = accumulator row) -> per-warp smem transpose buffer -> global with
+        // lane = column, so every store / red instruction covers one contiguous 128-byte line of C.
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
-        const bool vec_ok = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int split = u % g.splits;
             const int tile = u / g.splits;
             const int m0 = (tile / g.num_n) * BM;
             const int n0 = (tile % g.num_n) * BN;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const int row = m0 + quarter * 32 + lane;
+            const int rbase = m0 + quarter * 32;
             const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
+            const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);     // warp-collective: no divergence above
-                const int col0 = n0 + c * 32;
-                if (row < g.M && col0 < g.N) {
-                    float* crow = e.C + (long)row * e.ldc;
-                    if (e.accumulate) {
+                const int col = n0 + c * 32 + lane;
+                if (rbase < g.M && n0 + c * 32 < g.N) {              // warp-uniform
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < g.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
-                    } else {
-#pragma unroll
-                        for (int j4 = 0; j4 < 32; j4 += 4) {
-                            const int col = col0 + j4;
-                            if (vec_ok && col + 3 < g.N) {
-                                float4 v;
-                                v.x = pd_epi_value(e, row, col + 0, __uint_as_float(r[j4 + 0]));
-                                v.y = pd_epi_value(e, row, col + 1, __uint_as_float(r[j4 + 1]));
-                                v.z = pd_epi_value(e, row, col + 2, __uint_as_float(r[j4 + 2]));
-                                v.w = pd_epi_value(e, row, col + 3, __uint_as_float(r[j4 + 3]));
-                                *reinterpret_cast<float4*>(crow + col) = v;
+                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int rows = min(32, g.M - rbase);
+                    if (col < g.N) {
+                        const float bv = (extras && e.bias) ? __ldg(e.bias + col) : 0.f;
+                        for (int rr = 0; rr < rows; ++rr) {
+                            const int row = rbase + rr;
+                            float v = stg[rr * 33 + lane];
+                            float* cp = e.C + (long)row * e.ldc + col;
+                            if (extras) {
+                                v += bv;
+                                if (e.R) v += __ldg(e.R + (long)(row / e.r_div) * e.ldr + col);
+                            }
+                            if (e.accumulate) {
+                                atomicAdd(cp, v);
                             } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (col + j < g.N)
-                                        crow[col + j] = pd_epi_value(e, row, col + j, __uint_as_float(r[j4 + j]));
+                                if (e.act == PD_ACT_ELU) v = pd_elu(v);
+                                if (e.round_out) v = pd_tf32(v);
+                                *cp = v;
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -341,6 +347,27 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     }
     int tiles = g.num_m * g.num_n;
     int splits = 1;
+    g.extras_on_split0 = 0;
+    // Skinny-M layers (the per-timestep RSSM GEMMs, M = B*I = 50) have too few output tiles to pull their
+    // weights through more than a handful of SMs: split K over the idle SMs.  C is zeroed, every split adds its
+    // partial product with red.global.add, split 0 also adds bias + residual.
+    if (!epi.accumulate && g.num_m == 1 && epi.act == PD_ACT_NONE && !epi.round_out && tiles * 2 <= h->num_sms &&
+        g.kb_total >= 8) {
+        int want = h->num_sms / tiles;
+        int max_splits = g.kb_total / 4;
+        if (want > max_splits) want = max_splits;
+        if (want > 1) {
+            splits = want;
+            g.extras_on_split0 = 1;
+            g.epi.accumulate = 1;
+            if (epi.R == epi.C) {
+                g.epi.R = nullptr;                       // in-place residual: C already holds it, do not clear
+            } else {
+                cudaError_t me = cudaMemset2DAsync(epi.C, (size_t)epi.ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+                if (me != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "cudaMemset2DAsync: %s", cudaGetErrorString(me));
+            }
+        }
+    }
     if (epi.accumulate && tiles < h->num_sms) {
         // split-K: spread the contraction over idle SMs, keep >= 8 k-blocks per unit
         splits = h->num_sms / tiles;

@@ -16,6 +16,7 @@ so `loss.backward()` in the caller works unchanged.  Parameters live in one flat
 is what the fused optimizer and the single-bucket data-parallel all-reduce operate on.
 """
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -289,6 +290,7 @@ class Dreamer(nn.Module):
         self._arena = None
         self._arena_device = None
         self._ws = {}
+        self._graphs = {}
         self._ops = None
         self._weights_dirty = True
         self._dp = None           # optional data-parallel reducer (pydreamer_b200.parallel)
@@ -338,6 +340,7 @@ class Dreamer(nn.Module):
         self._arena, self._garena, self._arena_device = arena, garena, dev
         self._sarena = torch.zeros_like(arena)     # tf32-rounded shadow of the arena (GEMM operands)
         self._ws = {}
+        self._graphs = {}
         self._ops = None
         self._weights_dirty = True
 
@@ -538,17 +541,12 @@ class Dreamer(nn.Module):
         self._ensure_arena()
         want_grad = torch.is_grad_enabled()
         with torch.no_grad():
-            self._prepare_weights()
-            N = T * B * I
-            if noise is None:
-                noise = self._draw_noise(T, B * I, N, H)
             if want_grad:
-                self.ops.fill(self._garena, 0.0)
-            wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"])
-            if want_grad:
-                self._wm_backward(obs, T, B, I, H)
-            self._dream(T, B, I, H, noise["actor"], noise["prior"])
-            ac_out = self._actor_critic(T, B, I, H, want_grad)
+                self._sync_target_critic()
+            if self.use_cuda_graph and noise is None and want_grad and self._arena.is_cuda:
+                wm_out, ac_out = self._graphed_core(obs, in_state, T, B, I, H)
+            else:
+                wm_out, ac_out = self._core(obs, in_state, T, B, I, H, noise, want_grad)
         loss_model, loss_probe = wm_out["loss_model"], self.probe_model.dummy.detach() ** 2
         loss_actor, loss_critic = ac_out["loss_actor"], ac_out["loss_critic"]
         if want_grad:
@@ -561,6 +559,69 @@ class Dreamer(nn.Module):
         tensors = dict(wm_out["tensors"])
         tensors.update(policy_value=ac_out["value"][0].reshape(T, B, I).mean(-1))
         return (loss_model, loss_probe, loss_actor, loss_critic), wm_out["out_state"], metrics, tensors, {}
+
+    def _core(self, obs, in_state, T, B, I, H, noise, want_grad, force_weights=False):
+        """The kernel schedule of one step: weights prep, WM forward (+backward), dream, actor-critic (+backward)."""
+        if force_weights:
+            self._weights_dirty = True
+        self._prepare_weights()
+        N = T * B * I
+        if noise is None:
+            noise = self._draw_noise(T, B * I, N, H)
+        if want_grad:
+            self.ops.fill(self._garena, 0.0)
+        wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"])
+        if want_grad:
+            self._wm_backward(obs, T, B, I, H)
+        self._dream(T, B, I, H, noise["actor"], noise["prior"])
+        ac_out = self._actor_critic(T, B, I, H, want_grad)
+        return wm_out, ac_out
+
+    def _sync_target_critic(self):
+        """a2c.py:76-79: copy critic -> critic_target every target_interval calls (host-side counter)."""
+        ac = self.ac
+        if ac.train_steps % self.conf.target_interval == 0:
+            self._group_slice("target", self._arena).copy_(self._group_slice("critic", self._arena))
+            self._weights_dirty = True
+        ac.train_steps += 1
+
+    # set PD_B200_GRAPHS=0 to launch every kernel from Python instead of replaying a captured CUDA graph
+    use_cuda_graph = os.environ.get("PD_B200_GRAPHS", "1") != "0"
+
+    def _graphed_core(self, obs, in_state, T, B, I, H):
+        """CUDA-graph replay of `_core` (the ~1 400 kernel launches of a step are issued by one cudaGraphLaunch).
+        Calls 1-2 for a shape run eagerly (allocates the workspace, loads the kernels); call 3 captures."""
+        key = (T, B, I, H) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(obs.items()))
+        st = self._graphs.setdefault(key, dict(calls=0, graph=None))
+        st["calls"] += 1
+        if st["graph"] is None and (st["calls"] <= 2 or st.get("failed")):
+            return self._core(obs, in_state, T, B, I, H, None, True)
+        if st["graph"] is None:
+            st["obs"] = {k: torch.empty_like(v) for k, v in obs.items()}
+            st["state"] = tuple(torch.empty_like(s_) for s_ in in_state)
+            for k, v in obs.items():
+                st["obs"][k].copy_(v)
+            for d_, s_ in zip(st["state"], in_state):
+                d_.copy_(s_)
+            torch.cuda.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["out"] = self._core(st["obs"], st["state"], T, B, I, H, None, True, force_weights=True)
+                st["graph"] = g
+            except Exception as e:                           # keep running eagerly (same kernels), say so once
+                st["failed"] = True
+                import warnings
+                warnings.warn(f"pydreamer_b200: CUDA graph capture failed ({e}); continuing with eager launches")
+                torch.cuda.synchronize()
+                return self._core(obs, in_state, T, B, I, H, None, True)
+        else:
+            for k, v in obs.items():
+                st["obs"][k].copy_(v, non_blocking=True)
+            for d_, s_ in zip(st["state"], in_state):
+                d_.copy_(s_, non_blocking=True)
+        st["graph"].replay()
+        return st["out"]
 
     # ------------------------------------------------------------------ world model forward
     def _wm_forward(self, obs, in_state, T, B, I, H, noise_post):
@@ -870,11 +931,6 @@ class Dreamer(nn.Module):
         N = T * B * I
         J = H + 1
         b = self._buf
-        if want_grad:                                   # log_only=False path: target sync + counter (a2c.py:76-79)
-            if ac.train_steps % conf.target_interval == 0:
-                self._group_slice("target", self._arena).copy_(self._group_slice("critic", self._arena))
-                self._group_slice("target", self._sarena).copy_(self._group_slice("critic", self._sarena))
-            ac.train_steps += 1
         feats = b("feats", J, N, d.F)
         fall = feats.view(J * N, d.F)
         rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)

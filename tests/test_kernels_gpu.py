@@ -98,6 +98,25 @@ def test_gemm_splitk_accumulate_both_mn_major(ops, ref, impl, M, N, K):
     assert torch.equal(C, Cr), f"max diff {(C - Cr).abs().max().item()}"
 
 
+@pytest.mark.parametrize("impl", [1, 0])
+def test_gemm_skinny_m_splitk_with_bias_and_residual(ops, ref, impl):
+    """M = 50 rows (one RSSM timestep): the tcgen05 path splits K over the idle SMs; split 0 adds bias+residual."""
+    ops.set_gemm_impl(impl)
+    for (M, N, K, I) in [(50, 1000, 1024, 1), (50, 6144, 2048, 1), (48, 1000, 2048, 4), (50, 2048, 6144, 1)]:
+        A, B, bias, res = ints(M, K, seed=1), ints(N, K, seed=2), ints(N, seed=3), ints(M // I, N, seed=4)
+        big = torch.full((M, N + 40), 7.0, device=DEV)
+        C = big[:, 8:8 + N]
+        Cr = torch.empty(M, N, device=DEV)
+        ops.gemm(A, B, C, bias=bias, res=res, r_div=I)
+        ref.gemm(A, B, Cr, bias=bias, res=res, r_div=I)
+        assert torch.equal(C, Cr) and (big[:, :8] == 7).all() and (big[:, 8 + N:] == 7).all()
+        Bt = B.t().contiguous()                           # dX form, B MN-major, in-place residual (C += A B)
+        C2 = ints(M, N, seed=5); C2r = C2.clone(); keep = C2.clone()
+        ops.gemm(A, Bt, C2, b_mn=True, res=C2)
+        ref.gemm(A, Bt, C2r, b_mn=True, res=keep)
+        assert torch.equal(C2, C2r)
+
+
 def test_gemm_tf32_error_on_random_operands(ops, native_ops):
     if DEV == "cpu":
         pytest.skip("dry run")
@@ -238,8 +257,9 @@ def test_kl(ops, ref, mode):
         close(res["n"][2], d(post).entropy(), 3e-5, 1e-5, "entropy")
 
 
-def test_conv_data_movement_against_torch_conv(ops, ref):
-    NB, Cin, Cout, k = 6, 5, 8, 4
+@pytest.mark.parametrize("Cin,Cout", [(5, 8), (8, 12)])       # second case takes the float4 (C % 4 == 0) paths
+def test_conv_data_movement_against_torch_conv(ops, ref, Cin, Cout):
+    NB, k = 6, 4
     x = rnd(NB, Cin, 14, 14)
     w = rnd(Cout, Cin, k, k, seed=1)
     b = rnd(Cout, seed=2)
