@@ -24,14 +24,14 @@ constexpr int BM = 128;           // UMMA M
 constexpr int BN = 128;           // UMMA N
 constexpr int BK = 32;            // fp32 elements per k-block = 128 B = one swizzle row
 constexpr int UMMA_K = 8;         // tf32: 32 B per instruction
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 constexpr int B_BYTES = BN * BK * 4;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;   // 256 (power of two)
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_STAGING = 4 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose buffers
+constexpr int EPI_STAGING = 4 * 2 * 4096;      // per epilogue warp: two 32x32 fp32 swizzled TMA-store boxes
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGING;
 
 struct GemmArgs {
@@ -39,6 +39,7 @@ struct GemmArgs {
     int a_mn, b_mn;
     int num_m, num_n, splits, kb_total, kb_per_split;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
+    int tma_store;             // C is TMA-addressable: epilogue uses cp.async.bulk.tensor store / reduce
     int extras_on_split0;      // split-K of a plain (non-accumulate) GEMM: split 0 adds bias/residual, C pre-zeroed
     PdEpilogue epi;
 };
@@ -122,11 +123,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_STAGING);
     uint64_t* full = bars;                       // [STAGES]
     uint64_t* empty = bars + STAGES;             // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;         // [ACC_STAGES]
@@ -139,6 +140,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -231,12 +233,17 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        // TMEM -> registers (thread = accumulator row) -> per-warp smem transpose buffer -> global with
-        // lane = column, so every store / red instruction covers one contiguous 128-byte line of C.
+        // TMEM -> registers (thread = accumulator row, 32 consecutive columns) -> bias / residual / ELU / tf32 round
+        // in registers -> 128B-swizzled smem box (32 rows x 32 cols) -> TMA store (cp.async.bulk.tensor) or, for
+        // accumulate / split-K, TMA reduce-add (cp.reduce.async.bulk.tensor .add): the copy engine does the
+        // addressing, coalescing and M/N edge clipping; the warp issues ~60 instructions per 4 KB of output.
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
-        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
+        uint8_t* stg0 = smem + STAGES * STAGE_BYTES + (warp - 2) * (2 * 4096);
+        float* stgf = reinterpret_cast<float*>(stg0);     // scalar fallback view (pitch 33 floats fits in 8 KB)
+        int sbuf = 0;
+        const bool r_vec = e.R && ((e.ldr & 3) == 0) && ((((uintptr_t)e.R) & 15) == 0);
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int split = u % g.splits;
             const int tile = u / g.splits;
@@ -245,34 +252,92 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const int rbase = m0 + quarter * 32;
+            const int row = rbase + lane;
             const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
             const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);     // warp-collective: no divergence above
-                const int col = n0 + c * 32 + lane;
-                if (rbase < g.M && n0 + c * 32 < g.N) {              // warp-uniform
+                const int col0 = n0 + c * 32;
+                if (rbase >= g.M || col0 >= g.N) continue;           // warp-uniform
+                if (g.tma_store) {
+                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (extras) {
+                        if (e.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < g.N) ? __ldg(e.bias + col0 + j) : 0.f;
+                        }
+                        if (e.R && row < g.M) {
+                            const float* rp = e.R + (long)(row / e.r_div) * e.ldr + col0;
+                            if (r_vec && col0 + 32 <= g.N) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
+                                    v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (col0 + j < g.N) v[j] += __ldg(rp + j);
+                            }
+                        }
+                    }
+                    if (e.act == PD_ACT_ELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = pd_elu(v[j]);
+                    }
+                    if (e.round_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
+                    }
+                    uint8_t* buf = stg0 + sbuf * 4096;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer free again?
                     __syncwarp();
+                    const uint32_t rowaddr = smem_u32(buf) + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                     // SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7)
+                        const uint32_t a = rowaddr + (uint32_t)((j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (e.accumulate)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    sbuf ^= 1;
+                } else {
+                    // generic fallback (C not TMA-addressable: ldc % 4 != 0, e.g. N = 1 / 18 outputs)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stgf[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int col = col0 + lane;
                     const int rows = min(32, g.M - rbase);
                     if (col < g.N) {
                         const float bv = (extras && e.bias) ? __ldg(e.bias + col) : 0.f;
                         for (int rr = 0; rr < rows; ++rr) {
-                            const int row = rbase + rr;
-                            float v = stg[rr * 33 + lane];
-                            float* cp = e.C + (long)row * e.ldc + col;
+                            const int rw = rbase + rr;
+                            float x = stgf[rr * 33 + lane];
+                            float* cp = e.C + (long)rw * e.ldc + col;
                             if (extras) {
-                                v += bv;
-                                if (e.R) v += __ldg(e.R + (long)(row / e.r_div) * e.ldr + col);
+                                x += bv;
+                                if (e.R) x += __ldg(e.R + (long)(rw / e.r_div) * e.ldr + col);
                             }
                             if (e.accumulate) {
-                                atomicAdd(cp, v);
+                                atomicAdd(cp, x);
                             } else {
-                                if (e.act == PD_ACT_ELU) v = pd_elu(v);
-                                if (e.round_out) v = pd_tf32(v);
-                                *cp = v;
+                                if (e.act == PD_ACT_ELU) x = pd_elu(x);
+                                if (e.round_out) x = pd_tf32(x);
+                                *cp = x;
                             }
                         }
                     }
@@ -284,6 +349,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&tempty[as]);
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // all stores/reductions landed
     }
 
     tc_fence_before();
@@ -326,7 +392,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
         h->gemm_smem_configured = 1;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     int rc;
     if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     else       rc = make_map(h, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -344,6 +410,13 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     if (const char* dbg = getenv("PD_GEMM_MN_DESC")) {   // bring-up aid: "lbo,sbo" in bytes
         unsigned a = 0, b = 0;
         if (sscanf(dbg, "%u,%u", &a, &b) == 2) { g.mn_lbo = a; g.mn_sbo = b; }
+    }
+    g.tma_store = ((epi.ldc % 4) == 0) && ((((uintptr_t)epi.C) & 15) == 0);
+    if (g.tma_store) {
+        rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    } else {
+        tmC = tmA;
     }
     int tiles = g.num_m * g.num_n;
     int splits = 1;
@@ -379,7 +452,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units
     int units = tiles * g.splits;
     int grid = units < h->num_sms ? units : h->num_sms;
-    pd_gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, g);
+    pd_gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel");
     return PD_OK;
 }

@@ -259,6 +259,7 @@ def test_kl(ops, ref, mode):
 
 @pytest.mark.parametrize("Cin,Cout", [(5, 8), (8, 12)])       # second case takes the float4 (C % 4 == 0) paths
 def test_conv_data_movement_against_torch_conv(ops, ref, Cin, Cout):
+    torch.backends.cudnn.allow_tf32 = False      # the torch reference conv must be true fp32 for a 1e-5 comparison
     NB, k = 6, 4
     x = rnd(NB, Cin, 14, 14)
     w = rnd(Cout, Cin, k, k, seed=1)
