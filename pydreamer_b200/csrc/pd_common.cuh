@@ -21,6 +21,8 @@ struct pd_handle {
     char err[512];
     void* encode_tiled;       // cuTensorMapEncodeTiled entry point
     int gemm_smem_configured;
+    int gemm_2cta;            // allow the cta_group::2 256x256 kernel for large problems
+    int gemm2_smem_configured;
     int round_ops;            // round tensor-core operands to tf32 (rna) where they are produced
 };
 

@@ -59,10 +59,76 @@ pd_gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, long sAm, 
         }
     }
 }
+
+// y[m, n] = sum_k A[m, k] * B[n, k]  for N <= 4 (scalar heads): one warp per row, HBM-bound on A.
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(int M, int N, int K, const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,
+                 PdEpilogue e) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* a = A + row * lda;
+    for (int k = lane; k < K; k += 32) {
+        const float av = a[k];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) if (n < N) acc[n] = fmaf(av, __ldg(B + (long)n * ldb + k), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        if (n < N) {
+            float v = pd_warp_sum(acc[n]);
+            if (lane == 0) e.C[row * e.ldc + n] = pd_epi_value(e, (int)row, n, v);
+        }
+    }
+}
+
+// C[m, n] += sum_k A[k, m] * B[k, n]  for M <= 4 (weight gradient of a scalar head): blockDim (32, 8), a warp owns
+// 32 consecutive n; rows k are strided over blockIdx.y.
+__global__ void wcolsum_kernel(int M, int N, long K, const float* __restrict__ A, long lda, const float* __restrict__ B,
+                               long ldb, float* C, long ldc) {
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+        for (long k = (long)blockIdx.y * blockDim.y + threadIdx.y; k < K; k += (long)gridDim.y * blockDim.y) {
+            const float bv = B[k * ldb + n];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) if (m < M) acc[m] = fmaf(__ldg(A + k * lda + m), bv, acc[m]);
+        }
+    }
+    __shared__ float sh[4][8][33];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) sh[m][threadIdx.y][threadIdx.x] = acc[m];
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        for (int m = 0; m < M; ++m) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += sh[m][i][threadIdx.x];
+            atomicAdd(C + (long)m * ldc + n, s);
+        }
+    }
+}
 }  // namespace
 
 int pd_gemm_simt_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
                         long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream) {
+    if (h->gemm_impl != PD_GEMM_SIMT) {      // shape-specialised paths of the product (the validation arm stays generic)
+        if (!epi.accumulate && N <= 4 && !a_mn && !b_mn) {
+            gemv_rows_kernel<<<pd_cdiv(M, 8), 256, 0, stream>>>(M, N, K, A, lda, B, ldb, epi);
+            PD_CHECK_LAUNCH(h, "gemv_rows_kernel");
+            return PD_OK;
+        }
+        if (epi.accumulate && M <= 4 && a_mn && b_mn) {
+            long gy = (K + 63) / 64;
+            long cap = (long)h->num_sms * 8 / ((N + 31) / 32);
+            if (cap < 1) cap = 1;
+            if (gy > cap) gy = cap;
+            wcolsum_kernel<<<dim3((N + 31) / 32, (unsigned)gy), dim3(32, 8), 0, stream>>>(M, N, K, A, lda, B, ldb, epi.C, epi.ldc);
+            PD_CHECK_LAUNCH(h, "wcolsum_kernel");
+            return PD_OK;
+        }
+    }
     long sAm = a_mn ? 1 : lda, sAk = a_mn ? lda : 1;
     long sBn = b_mn ? 1 : ldb, sBk = b_mn ? ldb : 1;
     int gx = pd_cdiv(N, TN), gy = pd_cdiv(M, TM), gz = 1;

@@ -360,6 +360,262 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// =====================================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a thread-block cluster of two CTAs (one TPC) computes a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 n-rows); the leader CTA's elected
+// thread issues one tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 8) that reads both CTAs' shared memory and writes
+// 128 x 256 accumulators into each CTA's TMEM.  Per CTA and k-block the pair moves 32 KB from L2 for 128 x 256 outputs
+// — half the L2 traffic per FLOP of the 1-CTA 128 x 128 kernel, which is L2-bandwidth-bound at TF32 operand width.
+// =====================================================================================================================
+constexpr int BN2 = 256;                       // pair tile N (UMMA N)
+constexpr int BNH = 128;                       // B rows staged per CTA
+constexpr int STAGES2 = 4;
+constexpr int STAGE2_BYTES = A_BYTES + BNH * BK * 4;        // 32 KB
+constexpr int TMEM_COLS2 = ACC_STAGES * BN2;   // 512: the whole TMEM
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_STAGING;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint32_t leader_bar, void* smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {     // arrives on this barrier offset in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + STAGES2 * STAGE2_BYTES + EPI_STAGING);
+    uint64_t* full = bars;                       // [STAGES2]   (only the leader's are waited on)
+    uint64_t* empty = bars + STAGES2;            // [STAGES2]
+    uint64_t* tfull = bars + 2 * STAGES2;        // [ACC_STAGES]
+    uint64_t* tempty = bars + 2 * STAGES2 + ACC_STAGES;   // (only the leader's are waited on)
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES2 + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
+        for (int i = 0; i < STAGES2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS2)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                          // barrier inits + TMEM of both CTAs visible before any cross-CTA traffic
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m2 = (g.M + 255) / 256;
+    const int num_n2 = (g.N + BN2 - 1) / BN2;
+    const int units = num_m2 * num_n2 * g.splits;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = pair; u < units; u += npairs) {
+                const int split = u % g.splits;
+                const int tile = u / g.splits;
+                const int m0 = (tile / num_n2) * 256 + (int)rank * BM;        // this CTA's 128 rows of A / C
+                const int n0 = (tile % num_n2) * BN2 + (int)rank * BNH;       // this CTA's half of the B tile
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE2_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    const uint32_t lbar = smem_u32(&full[stage]) & PEER_MASK;  // the leader's barrier collects both CTAs' bytes
+                    if (leader) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    const int k0 = kb * BK;
+                    if (!g.a_mn) {
+                        tma_load_2d_2sm(&tmA, lbar, sa, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j) tma_load_2d_2sm(&tmA, lbar, sa + j * 4096, m0 + j * 32, k0);
+                    }
+                    if (!g.b_mn) {
+                        tma_load_2d_2sm(&tmB, lbar, sb, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BNH / 32; ++j) tma_load_2d_2sm(&tmB, lbar, sb + j * 4096, n0 + j * 32, k0);
+                    }
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) |
+                                   ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int u = pair; u < units; u += npairs) {
+                const int split = u % g.splits;
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * BN2);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int s = 0; s < BK / UMMA_K; ++s) {
+                        const uint64_t ad = g.a_mn ? make_desc(sa + s * 1024, g.mn_lbo, g.mn_sbo, 1)
+                                                   : make_desc(sa + s * 32, 16, 1024, 2);
+                        const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, g.mn_lbo, g.mn_sbo, 1)
+                                                   : make_desc(sb + s * 32, 16, 1024, 2);
+                        tc_mma_tf32_2sm(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                    }
+                    tc_commit_2sm(&empty[stage]);      // frees the stage in BOTH CTAs
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2sm(&tfull[as]);             // both CTAs' epilogues may read their accumulator halves
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs; same scheme as the 1-CTA kernel) =====================
+        const int quarter = warp & 3;
+        int as = 0; uint32_t aphase = 0;
+        const PdEpilogue& e = g.epi;
+        uint8_t* stg0 = smem + STAGES2 * STAGE2_BYTES + (warp - 2) * (2 * 4096);
+        int sbuf = 0;
+        const bool r_vec = e.R && ((e.ldr & 3) == 0) && ((((uintptr_t)e.R) & 15) == 0);
+        uint32_t leader_tempty[ACC_STAGES];
+#pragma unroll
+        for (int i = 0; i < ACC_STAGES; ++i) leader_tempty[i] = smem_u32(&tempty[i]) & PEER_MASK;
+        for (int u = pair; u < units; u += npairs) {
+            const int split = u % g.splits;
+            const int tile = u / g.splits;
+            const int m0 = (tile / num_n2) * 256 + (int)rank * BM;
+            const int n0 = (tile % num_n2) * BN2;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const int rbase = m0 + quarter * 32;
+            const int row = rbase + lane;
+            const uint32_t tbase = tmem_base + (uint32_t)(as * BN2) + ((uint32_t)(quarter * 32) << 16);
+            const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
+#pragma unroll 1
+            for (int c = 0; c < BN2 / 32; ++c) {
+                uint32_t r[32];
+                tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);
+                const int col0 = n0 + c * 32;
+                if (rbase >= g.M || col0 >= g.N) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (extras) {
+                    if (e.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += (col0 + j < g.N) ? __ldg(e.bias + col0 + j) : 0.f;
+                    }
+                    if (e.R && row < g.M) {
+                        const float* rp = e.R + (long)(row / e.r_div) * e.ldr + col0;
+                        if (r_vec && col0 + 32 <= g.N) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
+                                v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (col0 + j < g.N) v[j] += __ldg(rp + j);
+                        }
+                    }
+                }
+                if (e.act == PD_ACT_ELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = pd_elu(v[j]);
+                }
+                if (e.round_out) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
+                }
+                uint8_t* buf = stg0 + sbuf * 4096;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t rowaddr = smem_u32(buf) + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t a = rowaddr + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                 : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (e.accumulate)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                sbuf ^= 1;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_tempty[as]);      // 4 warps x 2 CTAs -> the leader's MMA issuer
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                          // nobody frees TMEM / exits while the peer may still touch it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS2)
+                     : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -447,6 +703,35 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
         int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
+    }
+    // Large tiles-rich problems go to the 2-CTA (cta_group::2) 256x256 kernel; it needs a TMA-addressable C.
+    int use2 = h->gemm_2cta && g.tma_store && M >= 512 && N >= 256 && !g.extras_on_split0;
+    if (use2) {
+        int tiles2 = pd_cdiv(M, 256) * pd_cdiv(N, BN2);
+        int pairs_avail = h->num_sms / 2;
+        if (tiles2 * 2 < pairs_avail && !epi.accumulate) use2 = 0;          // too few pair-tiles to fill the chip
+        if (use2) {
+            // re-box B for the half tile (128 rows per CTA) — same box as the 1-CTA kernel, so tmB is reused as is
+            int splits2 = 1;
+            if (epi.accumulate && tiles2 < pairs_avail) {
+                splits2 = pairs_avail / tiles2;
+                int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
+                if (splits2 > max_splits) splits2 = max_splits;
+                if (splits2 < 1) splits2 = 1;
+            }
+            g.kb_per_split = pd_cdiv(g.kb_total, splits2);
+            g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
+            int units2 = tiles2 * g.splits;
+            int gridp = units2 < pairs_avail ? units2 : pairs_avail;
+            if (!h->gemm2_smem_configured) {
+                cudaError_t e2 = cudaFuncSetAttribute(pd_gemm_tf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+                if (e2 != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(2cta smem=%d): %s", SMEM2_BYTES, cudaGetErrorString(e2));
+                h->gemm2_smem_configured = 1;
+            }
+            pd_gemm_tf32_2cta_kernel<<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, g);
+            PD_CHECK_LAUNCH(h, "pd_gemm_tf32_2cta_kernel");
+            return PD_OK;
+        }
     }
     g.kb_per_split = pd_cdiv(g.kb_total, splits);
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units

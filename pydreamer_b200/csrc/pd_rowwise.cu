@@ -112,6 +112,67 @@ ln_elu_bwd_kernel(int M, int N, const float* __restrict__ dy, long lddy, const f
     }
 }
 
+// ------------------------------------------------------------------ LayerNorm + ELU, few rows (one RSSM timestep)
+// With M = B*I = 50 rows a warp-per-row kernel exposes only 50 warps of parallelism and a long per-lane dependency
+// chain; here a whole 256-thread block owns a row (<= 4 elements per thread, two block reductions).
+__global__ void __launch_bounds__(256)
+ln_elu_fwd_row_kernel(int N, const float* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, float* __restrict__ y, long ldy,
+                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int round_out) {
+    __shared__ float sh[33];
+    const int row = blockIdx.x, t = threadIdx.x;
+    const float* xr = x + (long)row * ldx;
+    float v[4], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { int c = t + 256 * i; v[i] = c < N ? xr[c] : 0.f; s += v[i]; }
+    const float mean = pd_block_sum(s, sh) / (float)N;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { int c = t + 256 * i; float d = c < N ? v[i] - mean : 0.f; q += d * d; }
+    const float rstd = 1.0f / sqrtf(pd_block_sum(q, sh) / (float)N + eps);
+    float* yr = y + (long)row * ldy;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = t + 256 * i;
+        if (c < N) yr[c] = pd_round_if(pd_elu((v[i] - mean) * rstd * gamma[c] + beta[c]), round_out);
+    }
+    if (t == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+__global__ void __launch_bounds__(256)
+ln_elu_bwd_row_kernel(int N, const float* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
+                      const float* __restrict__ y, long ldy, const float* __restrict__ gamma,
+                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dx,
+                      long lddx, float* dgamma, float* dbeta, float* dbias, int round_out) {
+    __shared__ float sh[33];
+    const int row = blockIdx.x, t = threadIdx.x;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float g[4], xh[4], dxh[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = t + 256 * i;
+        if (c < N) {
+            g[i] = dy[(long)row * lddy + c] * pd_elu_grad_from_out(y[(long)row * ldy + c]);
+            xh[i] = (x[(long)row * ldx + c] - mean) * rstd;
+            dxh[i] = g[i] * gamma[c];
+            s1 += dxh[i]; s2 += dxh[i] * xh[i];
+        } else { g[i] = xh[i] = dxh[i] = 0.f; }
+    }
+    const float c1 = pd_block_sum(s1, sh) / (float)N;
+    const float c2 = pd_block_sum(s2, sh) / (float)N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = t + 256 * i;
+        if (c < N) {
+            float d = rstd * (dxh[i] - c1 - xh[i] * c2);
+            dx[(long)row * lddx + c] = pd_round_if(d, round_out);
+            atomicAdd(dgamma + c, g[i] * xh[i]);
+            atomicAdd(dbeta + c, g[i]);
+            if (dbias) atomicAdd(dbias + c, d);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ GRU gates
 __global__ void gru_fwd_kernel(int M, int D, const float* __restrict__ gi, long ldgi, const float* __restrict__ gh,
                                long ldgh, const float* __restrict__ hprev, long ldh, float* __restrict__ hout,
@@ -291,6 +352,11 @@ int pd_ln_elu_fwd(pd_handle* h, int M, int N, const float* x, long ldx, const fl
                   float eps, float* y, long ldy, float* mean, float* rstd, void* stream) {
     PD_REQUIRE(h, N >= 1 && N <= 1024, "pd_ln_elu_fwd: N=%d unsupported (1..1024)", N);
     cudaStream_t s = (cudaStream_t)stream;
+    if (M <= 256) {
+        ln_elu_fwd_row_kernel<<<M, 256, 0, s>>>(N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops);
+        PD_CHECK_LAUNCH(h, "ln_elu_fwd_row");
+        return PD_OK;
+    }
     int grid = pd_cdiv(M, 4);
     if (N <= 416) ln_elu_fwd_kernel<13><<<grid, 128, 0, s>>>(M, N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops);
     else          ln_elu_fwd_kernel<32><<<grid, 128, 0, s>>>(M, N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops);
@@ -303,6 +369,12 @@ int pd_ln_elu_bwd(pd_handle* h, int M, int N, const float* dy, long lddy, const 
                   float* dgamma, float* dbeta, float* dbias, void* stream) {
     PD_REQUIRE(h, N >= 1 && N <= 1024, "pd_ln_elu_bwd: N=%d unsupported (1..1024)", N);
     cudaStream_t s = (cudaStream_t)stream;
+    if (M <= 256) {
+        ln_elu_bwd_row_kernel<<<M, 256, 0, s>>>(N, dy, lddy, x, ldx, y, ldy, gamma, mean, rstd, dx, lddx, dgamma, dbeta,
+                                               dbias, h->round_ops);
+        PD_CHECK_LAUNCH(h, "ln_elu_bwd_row");
+        return PD_OK;
+    }
     int grid = pd_cdiv(M, 4);
     int cap = 2 * h->num_sms;
     if (grid > cap) grid = cap;

@@ -50,7 +50,9 @@ def ref():
 
 
 GEMM_SHAPES = [(128, 128, 32), (128, 128, 256), (50, 1000, 1024), (300, 6144, 1000), (130, 264, 100), (64, 48, 48),
-               (257, 1000, 2048), (2500, 400, 3072), (900, 108, 48)]
+               (257, 1000, 2048), (2500, 400, 3072), (900, 108, 48),
+               # large enough for the 2-CTA (cta_group::2) 256x256 kernel when PD_GEMM_2CTA=1
+               (1024, 512, 256), (2500, 6144, 96), (640, 1000, 1000)]
 
 
 @pytest.mark.parametrize("impl", [1, 0])
@@ -86,7 +88,8 @@ def test_gemm_epilogue_bias_residual_elu_and_strided_views(ops, ref, impl):
 
 
 @pytest.mark.parametrize("impl", [1, 0])
-@pytest.mark.parametrize("M,N,K", [(108, 48, 90000), (1000, 2048, 2500), (400, 400, 40000), (48, 48, 5000)])
+@pytest.mark.parametrize("M,N,K", [(108, 48, 90000), (1000, 2048, 2500), (400, 400, 40000), (48, 48, 5000),
+                                   (1, 400, 37500), (3, 48, 5000), (1024, 2048, 2500)])
 def test_gemm_splitk_accumulate_both_mn_major(ops, ref, impl, M, N, K):
     """weight-gradient form: C[M,N] += sum_k A[k,m] B[k,n]"""
     ops.set_gemm_impl(impl)
