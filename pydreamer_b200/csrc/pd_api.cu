@@ -26,7 +26,7 @@ int pd_create(int device_ordinal, pd_handle** out) {
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     h->gemm_impl = PD_GEMM_TCGEN05;
     h->round_ops = 1;
-    h->gemm_2cta = 0;
+    h->gemm_2cta = 1;
     if (const char* e2 = getenv("PD_GEMM_2CTA")) h->gemm_2cta = atoi(e2);
     cudaSetDevice(device_ordinal);
     cudaDriverEntryPointQueryResult qres;
