@@ -325,6 +325,21 @@ def run_ours(args):
     step(dev_obs)
     torch.cuda.synchronize()
     prof, model.ops.gemm_profile = model.ops.gemm_profile, None
+
+    class PhaseTimer:
+        def __init__(self):
+            self.ev = [("start", torch.cuda.Event(enable_timing=True))]
+            self.ev[0][1].record()
+
+        def mark(self, name):
+            e = torch.cuda.Event(enable_timing=True); e.record(); self.ev.append((name, e))
+
+    model._phase_timer = pt = PhaseTimer()
+    step(dev_obs)
+    pt.mark("backward()+clip+adamw")
+    torch.cuda.synchronize()
+    model._phase_timer = None
+    phases = {n: round(a[1].elapsed_time(b), 3) for a, (n, b) in zip(pt.ev[:-1], pt.ev[1:])}
     model.use_cuda_graph = graphs_on
     if args.dump_gemm_profile and rank == 0:
         agg = {}
@@ -353,6 +368,7 @@ def run_ours(args):
         e2e=dict(value=e2e_per_s, unit="steps/s", h2d_bytes_per_step=obs_bytes(host), d2h_bytes_per_step=16,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=int(launches) * args.steps,
+        phases_ms_eager=phases,
         launches_per_step=int(launches),
         clocks=clocks,
         roofline=dict(bound="tensor", kernel="pd_gemm_tf32_kernel (tcgen05.mma kind::tf32)", achieved=achieved,

@@ -38,6 +38,7 @@ typedef struct pd_handle pd_handle;
 
 #define PD_GEMM_TCGEN05 0 /* tcgen05.mma kind::tf32 + TMA + TMEM (default, the product path) */
 #define PD_GEMM_SIMT 1    /* plain fp32 CUDA-core tile kernel: validation arm for the tests  */
+#define PD_GEMM_C_ZEROED 1 /* pd_gemm flags bit */
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int pd_create(int device_ordinal, pd_handle** out);
@@ -57,13 +58,14 @@ int pd_set_round_operands(pd_handle* h, int on);
  *   accumulate = 1: atomically adds into C (split-K over all SMs; bias/R/act must be off).
  * Replaces every nn.Linear / nn.GRUCell matmul and the conv/deconv contractions:
  * common.py:47-55, rssm.py:103-116,138-146, rnn.py:60-67, encoders.py:80-90, decoders.py:128-155.
+ * flags: PD_GEMM_C_ZEROED = the caller has already cleared C (skinny-M launches that split K skip their own clear).
  * TMA constraints (tcgen05 impl): lda/ldb multiples of 4 elements, base pointers 16-byte aligned. */
 int pd_gemm(pd_handle* h, int M, int N, int K,
             const float* A, long lda, int a_mn,
             const float* B, long ldb, int b_mn,
             float* C, long ldc,
             const float* bias, const float* R, long ldr, int r_div,
-            int act, int round_out, int accumulate, void* stream);
+            int act, int round_out, int accumulate, int flags, void* stream);
 
 /* ---- LayerNorm(eps, biased var, affine) + ELU -------------------------------------------- */
 /* y = ELU(LN(x)); saves per-row mean / rstd.  common.py:45-51, rssm.py:105,110,115,139-140,144-145. */

@@ -49,7 +49,7 @@ class RefOps:
 
     # ------------------------------------------------------------------ gemm
     def gemm(self, A, B, C, *, a_mn=False, b_mn=False, bias=None, res=None, r_div=1, act=ACT_NONE,
-             round_out=False, accumulate=False):
+             round_out=False, accumulate=False, c_zeroed=False):
         a = A.t() if a_mn else A
         b = B if b_mn else B.t()
         v = a @ b

@@ -59,14 +59,14 @@ int pd_set_round_operands(pd_handle* h, int on) {
 
 int pd_gemm(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn,
             float* C, long ldc, const float* bias, const float* R, long ldr, int r_div, int act, int round_out,
-            int accumulate, void* stream) {
+            int accumulate, int flags, void* stream) {
     if (!h) return PD_ERR_ARG;
     PD_REQUIRE(h, M > 0 && N > 0 && K > 0, "pd_gemm: bad shape %d %d %d", M, N, K);
     PD_REQUIRE(h, A && B && C, "pd_gemm: null operand");
     PD_REQUIRE(h, !(accumulate && (bias || R || act)), "pd_gemm: accumulate excludes bias/residual/act");
     PdEpilogue e;
     e.C = C; e.ldc = ldc; e.bias = bias; e.R = R; e.ldr = ldr; e.r_div = r_div > 0 ? r_div : 1;
-    e.act = act; e.round_out = round_out; e.accumulate = accumulate;
+    e.act = act; e.round_out = round_out; e.accumulate = accumulate; e.c_zeroed = (flags & PD_GEMM_C_ZEROED) ? 1 : 0;
     // Skinny / unaligned contractions (scalar heads N=1, action inputs K=18, ...) cannot be described
     // by a TMA tensor map (16-byte strides) and have no tensor-core work to speak of: CUDA cores.
     const bool tma_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) &&

@@ -109,6 +109,7 @@ struct PdEpilogue {
     int act;             // PD_ACT_NONE / PD_ACT_ELU
     int round_out;       // round result to tf32 precision
     int accumulate;      // 0: C = v ; 1: atomicAdd(C, v) (split-K safe, no bias/act)
+    int c_zeroed;        // caller cleared C already (lets a skinny-M split-K launch skip its memset)
 };
 
 __device__ __forceinline__ float pd_epi_value(const PdEpilogue& e, int row, int col, float acc) {

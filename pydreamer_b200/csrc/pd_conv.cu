@@ -26,6 +26,38 @@ __global__ void im2col_kernel(long total, int Hout, int Wout, int Cc, int k, int
     }
 }
 
+// Planar (NCHW-like, sX == 1) input: one thread moves the k contiguous x-taps of one (row, channel, kh): the first
+// conv layer (image NCHW) and the last deconv layer's backward (error image NCHW).
+template <int K_>
+__global__ void im2col_planar_kernel(long total, int Hout, int Wout, int Cc, int korder, const float* __restrict__ in,
+                                     long sN, long sY, long sC, float* __restrict__ col, long ldcol, int round_out) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int kh = (int)(idx % K_);
+        long t = idx / K_;
+        int c = (int)(t % Cc);
+        long row = t / Cc;
+        int ox = (int)(row % Wout);
+        long t2 = row / Wout;
+        int oy = (int)(t2 % Hout);
+        long n = t2 / Hout;
+        const float* src = in + n * sN + (long)c * sC + (long)(2 * oy + kh) * sY + 2 * ox;
+        float v[K_];
+#pragma unroll
+        for (int j = 0; j < K_; j += 2) {                       // 2*ox is even: 8-byte aligned pairs
+            const float2 p = *reinterpret_cast<const float2*>(src + j);
+            v[j] = pd_round_if(p.x, round_out); v[j + 1] = pd_round_if(p.y, round_out);
+        }
+        float* dst = col + row * ldcol;
+        if (korder == 1) {
+#pragma unroll
+            for (int j = 0; j < K_; ++j) dst[(c * K_ + kh) * K_ + j] = v[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < K_; ++j) dst[(kh * K_ + j) * Cc + c] = v[j];
+        }
+    }
+}
+
 // NHWC fast path: one thread moves 4 consecutive channels (16 B) of one tap.
 __global__ void im2col_v4_kernel(long total4, int Hout, int Wout, int C4, int k, const float* __restrict__ in,
                                  long sN, long sY, long sX, float* __restrict__ col, long ldcol, int round_out) {
@@ -210,6 +242,19 @@ int pd_im2col(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, int korder,
         im2col_v4_kernel<<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
             total / 4, Hout, Wout, Cc / 4, k, in, sN, sY, sX, col, ldcol, round_out && h->round_ops);
         PD_CHECK_LAUNCH(h, "im2col_v4");
+        return PD_OK;
+    }
+    const bool planar = sX == 1 && (k == 4 || k == 6) && (sN % 2) == 0 && (sY % 2) == 0 && (sC % 2) == 0 &&
+                        ((((uintptr_t)in)) & 7) == 0;
+    if (planar) {
+        long tp = total / k;
+        if (k == 4)
+            im2col_planar_kernel<4><<<grid_for(tp, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+                tp, Hout, Wout, Cc, korder, in, sN, sY, sC, col, ldcol, round_out && h->round_ops);
+        else
+            im2col_planar_kernel<6><<<grid_for(tp, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+                tp, Hout, Wout, Cc, korder, in, sN, sY, sC, col, ldcol, round_out && h->round_ops);
+        PD_CHECK_LAUNCH(h, "im2col_planar");
         return PD_OK;
     }
     im2col_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(

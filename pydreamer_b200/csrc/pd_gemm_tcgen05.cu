@@ -683,6 +683,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     if (!epi.accumulate && g.num_m == 1 && epi.act == PD_ACT_NONE && !epi.round_out && tiles * 2 <= h->num_sms &&
         g.kb_total >= 8) {
         int want = h->num_sms / tiles;
+        if (const char* ms = getenv("PD_GEMM_SKINNY_MAXSPLIT")) { int v = atoi(ms); if (want > v) want = v; }   // tuning aid
         int max_splits = g.kb_total / 4;
         if (want > max_splits) want = max_splits;
         if (want > 1) {
@@ -691,7 +692,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
             g.epi.accumulate = 1;
             if (epi.R == epi.C) {
                 g.epi.R = nullptr;                       // in-place residual: C already holds it, do not clear
-            } else {
+            } else if (!epi.c_zeroed) {
                 cudaError_t me = cudaMemset2DAsync(epi.C, (size_t)epi.ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
                 if (me != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "cudaMemset2DAsync: %s", cudaGetErrorString(me));
             }

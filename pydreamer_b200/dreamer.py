@@ -570,12 +570,25 @@ class Dreamer(nn.Module):
             noise = self._draw_noise(T, B * I, N, H)
         if want_grad:
             self.ops.fill(self._garena, 0.0)
+        tm = self._phase_timer
+        if tm is not None:
+            tm.mark("prepare+noise")
         wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"])
+        if tm is not None:
+            tm.mark("wm_forward")
         if want_grad:
             self._wm_backward(obs, T, B, I, H)
+        if tm is not None:
+            tm.mark("wm_backward")
         self._dream(T, B, I, H, noise["actor"], noise["prior"])
+        if tm is not None:
+            tm.mark("dream")
         ac_out = self._actor_critic(T, B, I, H, want_grad)
+        if tm is not None:
+            tm.mark("actor_critic")
         return wm_out, ac_out
+
+    _phase_timer = None       # bench.py installs a PhaseTimer (CUDA events between the phases of one eager step)
 
     def _sync_target_critic(self):
         """a2c.py:76-79: copy critic -> critic_target every target_interval calls (host-side counter)."""
@@ -667,20 +680,24 @@ class Dreamer(nn.Module):
         feats = b("feats", H + 1, N, d.F)            # feats[0] = world-model features, feats[1:] = dream
         feat = feats[0].view(T, BI, d.F)
         W = self._w
+        skinny = BI <= 128                      # the per-timestep GEMMs split K and reduce into C: clear all T slices at once
+        if skinny:
+            for buf_ in (x1, gi, gh, y2, post):
+                ops.fill(buf_, 0.0)
         for t in range(T):
             last = t == T - 1
             ops.gemm(zin[t], W(cell.z_mlp.weight), x1[t], bias=self._raw(cell.z_mlp.bias), res=aa[t * B:(t + 1) * B],
-                     r_div=I)
+                     r_div=I, c_zeroed=skinny)
             ops.ln_elu_fwd(x1[t], self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za[t], m1[t], r1[t])
-            ops.gemm(za[t], W(gru.weight_ih), gi[t], bias=self._raw(gru.bias_ih))
-            ops.gemm(hin[t], W(gru.weight_hh), gh[t], bias=self._raw(gru.bias_hh))
+            ops.gemm(za[t], W(gru.weight_ih), gi[t], bias=self._raw(gru.bias_ih), c_zeroed=skinny)
+            ops.gemm(hin[t], W(gru.weight_hh), gh[t], bias=self._raw(gru.bias_hh), c_zeroed=skinny)
             ops.gru_fwd(gi[t], gh[t], hin[t], feat[t, :, :d.D], None if last else hin[t + 1],
                         None if last else mask[t + 1], gates[t])
             ops.gemm(feat[t, :, :d.D], W(cell.post_mlp_h.weight), y2[t], bias=self._raw(cell.post_mlp_h.bias),
-                     res=ea[t * B:(t + 1) * B], r_div=I)
+                     res=ea[t * B:(t + 1) * B], r_div=I, c_zeroed=skinny)
             ops.ln_elu_fwd(y2[t], self._raw(cell.post_norm.weight), self._raw(cell.post_norm.bias), 1e-3, pin[t],
                            m2[t], r2[t])
-            ops.gemm(pin[t], W(cell.post_mlp.weight), post[t], bias=self._raw(cell.post_mlp.bias))
+            ops.gemm(pin[t], W(cell.post_mlp.weight), post[t], bias=self._raw(cell.post_mlp.bias), c_zeroed=skinny)
             ops.cat_sample(post[t], noise_post[t], d.G, d.C, feat[t, :, d.D:], None if last else zin[t + 1],
                            None if last else mask[t + 1], idx[t])
         featN = feats[0]                                   # (N, F)
@@ -829,23 +846,28 @@ class Dreamer(nn.Module):
         dpost = b("bwd.dpost", T, BI, d.Z)
         dy2, dx1 = b("bwd.dy2", T, BI, d.Hd), b("bwd.dx1", T, BI, d.Hd)
         dgi, dgh = b("bwd.dgi", T, BI, 3 * d.D), b("bwd.dgh", T, BI, 3 * d.D)
-        dpin, dza = b("bwd.dpin", BI, d.Hd), b("bwd.dza", BI, d.Hd)
-        dhp, dhc = b("bwd.dhp", BI, d.D), b("bwd.dhc", BI, d.D)
-        dhin, dzin = b("bwd.dhin", BI, d.D), b("bwd.dzin", BI, d.Z)
+        dpin, dza = b("bwd.dpin", T, BI, d.Hd), b("bwd.dza", T, BI, d.Hd)
+        dhp, dhc = b("bwd.dhp", T, BI, d.D), b("bwd.dhc", BI, d.D)
+        dhin, dzin = b("bwd.dhin", T, BI, d.D), b("bwd.dzin", T, BI, d.Z)
+        skinny = BI <= 128
+        if skinny:
+            for buf_ in (dpin, dza, dhp, dhin, dzin):
+                ops.fill(buf_, 0.0)
         for t in reversed(range(T)):
             nxt = t < T - 1
-            ops.cat_st_bwd(post[t], d.G, d.C, dfeat3[t, :, d.D:], dzin if nxt else None, mask[t + 1] if nxt else None,
-                           dpost_u[t], w3[t], conf.kl_weight, dpost[t])
-            ops.gemm(dpost[t], W(cell.post_mlp.weight), dpin, b_mn=True)
-            ops.ln_elu_bwd(dpin, y2[t], pin[t], self._raw(cell.post_norm.weight), m2[t], r2[t], dy2[t],
+            ops.cat_st_bwd(post[t], d.G, d.C, dfeat3[t, :, d.D:], dzin[t + 1] if nxt else None,
+                           mask[t + 1] if nxt else None, dpost_u[t], w3[t], conf.kl_weight, dpost[t])
+            ops.gemm(dpost[t], W(cell.post_mlp.weight), dpin[t], b_mn=True, c_zeroed=skinny)
+            ops.ln_elu_bwd(dpin[t], y2[t], pin[t], self._raw(cell.post_norm.weight), m2[t], r2[t], dy2[t],
                            G(cell.post_norm.weight), G(cell.post_norm.bias), G(cell.post_mlp_h.bias))
-            ops.gemm(dy2[t], W(cell.post_mlp_h.weight), dhp, b_mn=True, res=dfeat3[t, :, :d.D])
-            ops.gru_bwd(dhp, dhin if nxt else None, mask[t + 1] if nxt else None, gates[t], hin[t], dgi[t], dgh[t], dhc)
-            ops.gemm(dgh[t], W(gru.weight_hh), dhin, b_mn=True, res=dhc)
-            ops.gemm(dgi[t], W(gru.weight_ih), dza, b_mn=True)
-            ops.ln_elu_bwd(dza, x1[t], za[t], self._raw(cell.in_norm.weight), m1[t], r1[t], dx1[t],
+            ops.gemm(dy2[t], W(cell.post_mlp_h.weight), dhp[t], b_mn=True, res=dfeat3[t, :, :d.D], c_zeroed=skinny)
+            ops.gru_bwd(dhp[t], dhin[t + 1] if nxt else None, mask[t + 1] if nxt else None, gates[t], hin[t], dgi[t],
+                        dgh[t], dhc)
+            ops.gemm(dgh[t], W(gru.weight_hh), dhin[t], b_mn=True, res=dhc, c_zeroed=skinny)
+            ops.gemm(dgi[t], W(gru.weight_ih), dza[t], b_mn=True, c_zeroed=skinny)
+            ops.ln_elu_bwd(dza[t], x1[t], za[t], self._raw(cell.in_norm.weight), m1[t], r1[t], dx1[t],
                            G(cell.in_norm.weight), G(cell.in_norm.bias), G(cell.z_mlp.bias))
-            ops.gemm(dx1[t], W(cell.z_mlp.weight), dzin, b_mn=True)
+            ops.gemm(dx1[t], W(cell.z_mlp.weight), dzin[t], b_mn=True, c_zeroed=skinny)
         # batched weight gradients over all T*BI rows
         f2 = lambda x: x.view(N, x.shape[-1])
         ops.gemm(f2(dpost), f2(pin), G(cell.post_mlp.weight), a_mn=True, b_mn=True, accumulate=True)

@@ -73,7 +73,7 @@ class NativeOps:
 
     # ------------------------------------------------------------------ gemm
     def gemm(self, A, B, C, *, a_mn=False, b_mn=False, bias=None, res=None, r_div=1, act=ACT_NONE,
-             round_out=False, accumulate=False):
+             round_out=False, accumulate=False, c_zeroed=False):
         """C[M,N] (=|+=) A(m,k) B(n,k).  A: [M,K] (or stored [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn)."""
         M, N = C.shape
         K = A.shape[0] if a_mn else A.shape[1]
@@ -85,7 +85,7 @@ class NativeOps:
             e0.record()
         rc = self.lib.pd_gemm(self.h, M, N, K, _ptr(A), _ld(A), int(a_mn), _ptr(B), _ld(B), int(b_mn),
                               _ptr(C), _ld(C), _ptr(bias), _ptr(res), _ld(res) if res is not None else 0,
-                              int(r_div), int(act), int(round_out), int(accumulate), self._s())
+                              int(r_div), int(act), int(round_out), int(accumulate), 1 if c_zeroed else 0, self._s())
         self._ck(rc, "pd_gemm")
         if prof is not None:
             e1.record()

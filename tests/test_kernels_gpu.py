@@ -279,6 +279,10 @@ def test_conv_data_movement_against_torch_conv(ops, ref, Cin, Cout):
         ops.set_gemm_impl(1)
         ops.gemm(col, wk, y, bias=b)
         close(y.view(NB, 6, 6, Cout).permute(0, 3, 1, 2), yref, 1e-5, 1e-5, f"conv korder {korder}")
+    xi = rnd(NB, 3, 16, 16, seed=9)                                           # planar input, k=6 (last deconv backward)
+    c6, c6r = torch.empty(NB * 36, 108, device=DEV), torch.empty(NB * 36, 108, device=DEV)
+    ops.im2col(xi.permute(0, 2, 3, 1), 6, 0, c6, round_out=False); ref.im2col(xi.permute(0, 2, 3, 1), 6, 0, c6r)
+    assert torch.equal(c6, c6r)
     # transposed conv = gemm + col2im  (decoders.py:149-155)
     wt = rnd(Cout, Cin, 5, 5, seed=3)   # ConvTranspose2d weight (in=Cout, out=Cin)
     bt = rnd(Cin, seed=4)

@@ -8,7 +8,7 @@ from pydreamer_b200.ops import NativeOps
 def main():
     reps = 20
     shapes = []
-    args = sys.argv[1:]
+    args = [a for a in sys.argv[1:] if a != '--chain']
     if "--reps" in args:
         i = args.index("--reps"); reps = int(args[i + 1]); del args[i:i + 2]
     for a in args:
@@ -17,6 +17,30 @@ def main():
         shapes.append(v)
     ops = NativeOps("cuda:0")
     out = []
+    if "--chain" in sys.argv:
+        # dependent chain of identical small GEMMs replayed from a CUDA graph: per-launch latency inside a step
+        args2 = [a for a in sys.argv[1:] if not a.startswith("--") and "," in a]
+        for a in args2:
+            v = [int(x) for x in a.split(",")] ; v += [0] * (8 - len(v))
+            M, N, K, a_mn, b_mn, acc, bias, res = v
+            A = torch.randn((M, K), device="cuda"); B = torch.randn((N, K), device="cuda")
+            Cs = [torch.zeros(M, N, device="cuda") for _ in range(2)]
+            bv = torch.randn(N, device="cuda") if bias else None
+            rv = torch.randn(M, N, device="cuda") if res else None
+            n = 200
+            def body():
+                for i in range(n):
+                    ops.gemm(A, B, Cs[i & 1], bias=bv, res=rv)
+            body(); torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            print(json.dumps(dict(chain=[M, N, K, bias, res], us_per_gemm=1000 * e0.elapsed_time(e1) / n,
+                                  maxsplit=os.environ.get("PD_GEMM_SKINNY_MAXSPLIT", ""))))
+        return
     for (M, N, K, a_mn, b_mn, acc, bias, res) in shapes:
         A = torch.randn((K, M) if a_mn else (M, K), device="cuda")
         B = torch.randn((K, N) if b_mn else (N, K), device="cuda")
