@@ -264,7 +264,8 @@ def training_step(sd, conf, obs, in_state, noise, iwae_samples=None, imag_horizo
                 tensors=tensors, inter=inter)
 
 
-def draw_noise(conf, T, B, I=None, H=None, generator=None, device="cpu", dtype=torch.float32):
+def draw_noise(conf, T, B, I=None, H=None, generator=None, device="cpu", dtype=torch.float32, image_pred=False,
+               dream_log=False):
     """Sampling noise in the reference's RNG consumption order: T posterior draws, then per
     imagination step the actor draw followed by the prior draw.  With the default CPU generator seeded like the
     reference run, the draws are the very numbers torch.multinomial consumes there."""
@@ -274,6 +275,9 @@ def draw_noise(conf, T, B, I=None, H=None, generator=None, device="cpu", dtype=t
     BI, N = B * I, T * B * I
     e = lambda *s: torch.empty(*s, dtype=torch.float32).exponential_(generator=generator)
     post = torch.stack([e(BI * G, C).reshape(BI, G * C) for _ in range(T)])
+    extra = {}
+    if image_pred:                                   # dreamer.py:385 prior sample, drawn inside wm.training_step
+        extra["image_pred"] = e(N * G, C).reshape(N, G * C)
     actor, prior = [], []
     for _ in range(H):
         if conf.actor_dist == "onehot":
@@ -281,5 +285,11 @@ def draw_noise(conf, T, B, I=None, H=None, generator=None, device="cpu", dtype=t
         else:
             actor.append(torch.empty(N, A).normal_(generator=generator))
         prior.append(e(N * G, C).reshape(N, G * C))
-    out = dict(post=post, actor=torch.stack(actor), prior=torch.stack(prior))
+    if dream_log:                                    # dreamer.py:169-170: (T-1)-step dream from the B first states
+        la, lp = [], []
+        for _ in range(T - 1):
+            la.append(e(B, A) if conf.actor_dist == "onehot" else torch.empty(B, A).normal_(generator=generator))
+            lp.append(e(B * G, C).reshape(B, G * C))
+        extra["dream_log_actor"], extra["dream_log_prior"] = torch.stack(la), torch.stack(lp)
+    out = dict(post=post, actor=torch.stack(actor), prior=torch.stack(prior), **extra)
     return {k: v.to(device=device, dtype=dtype) for k, v in out.items()}

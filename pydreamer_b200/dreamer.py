@@ -401,8 +401,37 @@ class Dreamer(nn.Module):
         dev = next(self.parameters()).device
         return (torch.zeros((batch_size, self.d.D), device=dev), torch.zeros((batch_size, self.d.Z), device=dev))
 
+    @torch.no_grad()
     def inference(self, obs, in_state):
-        raise NotImplementedError("Dreamer.inference (actor path, T=1) is row N2 of SURVEY.md §8(f): next")
+        """dreamer.py:92-111: one posterior step (T=1) + actor / critic forward for the env-interaction policy.
+        Returns (action distribution, out_state, {'policy_value'}) like the reference (generator.py:321-328)."""
+        import torch.distributions as D
+
+        assert "action" in obs, "Observation should contain previous action"
+        act_shape = obs["action"].shape
+        assert len(act_shape) == 3 and act_shape[0] == 1, f"Expected shape (1,B,A), got {act_shape}"
+        self._ensure_arena()
+        self._prepare_weights()
+        d, B = self.d, act_shape[1]
+        noise = self._buf("inf.noise", 1, B, d.Z).exponential_()
+        if getattr(self, "_test_inference_noise", None) is not None:      # tests pin the sampling noise
+            noise = self._test_inference_noise
+        feat = self._buf("inf.feat", 1, B, d.F)
+        _, _, _, out_state = self._wm_features(obs, in_state, 1, B, 1, noise, "inf.", feat)
+        f = feat.view(B, d.F)
+        alog, val = self._buf("inf.alog", B, d.Aout), self._buf("inf.val", B, 1)
+        self._mlp_fwd(self._mlp_params(self.ac.actor), f, alog, "scratch")
+        self._mlp_fwd(self._mlp_params(self.ac.critic), f, val, "scratch")
+        y = alog.view(1, B, d.Aout).clone()
+        if self.conf.actor_dist == "onehot":
+            dist = D.OneHotCategorical(logits=y)
+        else:                                                          # functions.py:69-78
+            mean = 5 * torch.tanh(y[..., :d.A] / 5)
+            std = torch.nn.functional.softplus(y[..., d.A:]) + 0.1
+            normal = D.independent.Independent(D.normal.Normal(mean, std), 1)
+            dist = D.TransformedDistribution(normal, [D.TanhTransform()])
+            dist.entropy = normal.entropy
+        return dist, out_state, dict(policy_value=val.mean())
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, *shape, dtype=torch.float32, zero=False):
@@ -511,7 +540,7 @@ class Dreamer(nn.Module):
                 ops.gemm(dx, self._w(mp.lin[0].weight), din, b_mn=True, res=din if din_accum else None)
 
     # ------------------------------------------------------------------ noise
-    def _draw_noise(self, T, BI, N, H):
+    def _draw_noise(self, T, BI, N, H, image_pred=False, dream_log=False, B=0):
         """Exp(1) noise for the categorical samples in the reference's consumption order (SURVEY.md App. D);
         Gaussian noise for the tanh_normal actor."""
         d, dev = self.d, self._arena.device
@@ -521,7 +550,14 @@ class Dreamer(nn.Module):
         else:
             actor = self._buf("noise.actor", H, N, d.A).normal_()
         prior = self._buf("noise.prior", H, N, d.Z).exponential_()
-        return dict(post=post, actor=actor, prior=prior)
+        out = dict(post=post, actor=actor, prior=prior)
+        if image_pred:
+            out["image_pred"] = self._buf("noise.image_pred", N, d.Z).exponential_()
+        if dream_log:
+            la = self._buf("noise.dl_actor", T - 1, B, d.A)
+            out["dream_log_actor"] = la.exponential_() if self.conf.actor_dist == "onehot" else la.normal_()
+            out["dream_log_prior"] = self._buf("noise.dl_prior", T - 1, B, d.Z).exponential_()
+        return out
 
     # ------------------------------------------------------------------ training step
     def training_step(self, obs, in_state, iwae_samples=None, imag_horizon=None, do_open_loop=False,
@@ -532,9 +568,6 @@ class Dreamer(nn.Module):
         assert "reward" in obs, "`reward` required in observation"
         assert "reset" in obs, "`reset` required in observation"
         assert "terminal" in obs, "`terminal` required in observation"
-        if do_open_loop or do_image_pred or do_dream_tensors:
-            raise NotImplementedError("evaluation/logging branches (do_open_loop, do_image_pred, do_dream_tensors) "
-                                      "are row N4 of SURVEY.md §8(f): next")
         I = int(iwae_samples or self.iwae_samples)
         H = int(imag_horizon or self.imag_horizon)
         T, B = obs["action"].shape[:2]
@@ -543,10 +576,13 @@ class Dreamer(nn.Module):
         with torch.no_grad():
             if want_grad:
                 self._sync_target_critic()
-            if self.use_cuda_graph and noise is None and want_grad and self._arena.is_cuda:
+            flags = (bool(do_open_loop), bool(do_image_pred), bool(do_dream_tensors and self.wm.decoder.image is not None))
+            if flags[0] and want_grad:
+                raise NotImplementedError("do_open_loop is the evaluation branch (train.py:353-359 runs it under no_grad)")
+            if self.use_cuda_graph and noise is None and want_grad and self._arena.is_cuda and not any(flags):
                 wm_out, ac_out = self._graphed_core(obs, in_state, T, B, I, H)
-            else:
-                wm_out, ac_out = self._core(obs, in_state, T, B, I, H, noise, want_grad)
+            else:                                   # logging / evaluation steps (~10 % of steps) are launched eagerly
+                wm_out, ac_out = self._core(obs, in_state, T, B, I, H, noise, want_grad, flags=flags)
         loss_model, loss_probe = wm_out["loss_model"], self.probe_model.dummy.detach() ** 2
         loss_actor, loss_critic = ac_out["loss_actor"], ac_out["loss_critic"]
         if want_grad:
@@ -558,34 +594,40 @@ class Dreamer(nn.Module):
         metrics = dict(wm_out["metrics"]); metrics.update(ac_out["metrics"])
         tensors = dict(wm_out["tensors"])
         tensors.update(policy_value=ac_out["value"][0].reshape(T, B, I).mean(-1))
-        return (loss_model, loss_probe, loss_actor, loss_critic), wm_out["out_state"], metrics, tensors, {}
+        return (loss_model, loss_probe, loss_actor, loss_critic), wm_out["out_state"], metrics, tensors, \
+            ac_out.get("dream_tensors", {})
 
-    def _core(self, obs, in_state, T, B, I, H, noise, want_grad, force_weights=False):
+    def _core(self, obs, in_state, T, B, I, H, noise, want_grad, force_weights=False, flags=(False, False, False)):
         """The kernel schedule of one step: weights prep, WM forward (+backward), dream, actor-critic (+backward)."""
         if force_weights:
             self._weights_dirty = True
         self._prepare_weights()
         N = T * B * I
+        open_loop, image_pred, dream_log = flags
         if noise is None:
-            noise = self._draw_noise(T, B * I, N, H)
+            noise = self._draw_noise(T, B * I, N, H, image_pred, dream_log, B)
         if want_grad:
             self.ops.fill(self._garena, 0.0)
         tm = self._phase_timer
         if tm is not None:
             tm.mark("prepare+noise")
-        wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"])
+        wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"], open_loop,
+                                  noise["image_pred"] if image_pred else None)
         if tm is not None:
             tm.mark("wm_forward")
         if want_grad:
             self._wm_backward(obs, T, B, I, H)
         if tm is not None:
             tm.mark("wm_backward")
-        self._dream(T, B, I, H, noise["actor"], noise["prior"])
+        feats = self._buf("feats", H + 1, N, self.d.F)
+        self._dream(feats, N, H, noise["actor"], noise["prior"], "")
         if tm is not None:
             tm.mark("dream")
-        ac_out = self._actor_critic(T, B, I, H, want_grad)
+        ac_out = self._actor_critic(feats, N, H, want_grad, "")
         if tm is not None:
             tm.mark("actor_critic")
+        if dream_log:
+            ac_out["dream_tensors"] = self._dream_for_log(obs, T, B, I, noise["dream_log_actor"], noise["dream_log_prior"])
         return wm_out, ac_out
 
     _phase_timer = None       # bench.py installs a PhaseTimer (CUDA events between the phases of one eager step)
@@ -637,16 +679,17 @@ class Dreamer(nn.Module):
         return st["out"]
 
     # ------------------------------------------------------------------ world model forward
-    def _wm_forward(self, obs, in_state, T, B, I, H, noise_post):
+    def _wm_features(self, obs, in_state, T, B, I, noise_post, tag, feat, open_loop=False):
+        """Encoder + posterior unroll (forward only).  `feat` (T, B*I, F) receives cat(h, z); every intermediate the
+        backward needs is kept in workspace buffers named `tag + ...`."""
         ops, d, conf = self.ops, self.d, self.conf
         NB, BI = T * B, B * I
         N = NB * I
         cd, IC = d.cd, d.IC
-        b = self._buf
+        b = lambda name, *shape, **kw: self._buf(tag + name, *shape, **kw)
         enc = self.wm.encoder.encoder_image.model
         cell = self.wm.core.cell
         gru = cell.gru.layers[0]
-
         # ---- encoder (encoders.py:72-96): im2col -> tcgen05 GEMM (+bias+ELU) x4, NHWC activations
         img = obs["image"].reshape(NB, IC, 64, 64)
         geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
@@ -677,8 +720,6 @@ class Dreamer(nn.Module):
         m2, r2 = b("rssm.m2", T, BI), b("rssm.r2", T, BI)
         post = b("rssm.post", T, BI, d.Z)
         idx = b("rssm.idx", T, BI, d.G, dtype=torch.int32)
-        feats = b("feats", H + 1, N, d.F)            # feats[0] = world-model features, feats[1:] = dream
-        feat = feats[0].view(T, BI, d.F)
         W = self._w
         skinny = BI <= 128                      # the per-timestep GEMMs split K and reduce into C: clear all T slices at once
         if skinny:
@@ -693,13 +734,32 @@ class Dreamer(nn.Module):
             ops.gemm(hin[t], W(gru.weight_hh), gh[t], bias=self._raw(gru.bias_hh), c_zeroed=skinny)
             ops.gru_fwd(gi[t], gh[t], hin[t], feat[t, :, :d.D], None if last else hin[t + 1],
                         None if last else mask[t + 1], gates[t])
-            ops.gemm(feat[t, :, :d.D], W(cell.post_mlp_h.weight), y2[t], bias=self._raw(cell.post_mlp_h.bias),
-                     res=ea[t * B:(t + 1) * B], r_div=I, c_zeroed=skinny)
-            ops.ln_elu_fwd(y2[t], self._raw(cell.post_norm.weight), self._raw(cell.post_norm.bias), 1e-3, pin[t],
-                           m2[t], r2[t])
-            ops.gemm(pin[t], W(cell.post_mlp.weight), post[t], bias=self._raw(cell.post_mlp.bias), c_zeroed=skinny)
+            if not open_loop:
+                ops.gemm(feat[t, :, :d.D], W(cell.post_mlp_h.weight), y2[t], bias=self._raw(cell.post_mlp_h.bias),
+                         res=ea[t * B:(t + 1) * B], r_div=I, c_zeroed=skinny)
+                ops.ln_elu_fwd(y2[t], self._raw(cell.post_norm.weight), self._raw(cell.post_norm.bias), 1e-3, pin[t],
+                               m2[t], r2[t])
+                ops.gemm(pin[t], W(cell.post_mlp.weight), post[t], bias=self._raw(cell.post_mlp.bias), c_zeroed=skinny)
+            else:                                   # open loop (rssm.py:52-53): the "posterior" is the prior, no embed
+                ops.gemm(feat[t, :, :d.D], W(cell.prior_mlp_h.weight), y2[t], bias=self._raw(cell.prior_mlp_h.bias),
+                         c_zeroed=skinny)
+                ops.ln_elu_fwd(y2[t], self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pin[t],
+                               m2[t], r2[t])
+                ops.gemm(pin[t], W(cell.prior_mlp.weight), post[t], bias=self._raw(cell.prior_mlp.bias), c_zeroed=skinny)
             ops.cat_sample(post[t], noise_post[t], d.G, d.C, feat[t, :, d.D:], None if last else zin[t + 1],
                            None if last else mask[t + 1], idx[t])
+        out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
+        return img, post, idx, out_state
+
+    def _wm_forward(self, obs, in_state, T, B, I, H, noise_post, open_loop=False, noise_image_pred=None):
+        ops, d, conf = self.ops, self.d, self.conf
+        NB, BI = T * B, B * I
+        N = NB * I
+        b, W = self._buf, self._w
+        cell = self.wm.core.cell
+        feats = b("feats", H + 1, N, d.F)            # feats[0] = world-model features, feats[1:] = dream
+        img, post, idx, out_state = self._wm_features(obs, in_state, T, B, I, noise_post, "", feats[0].view(T, BI, d.F),
+                                                      open_loop)
         featN = feats[0]                                   # (N, F)
         hN = featN[:, :d.D]
         # batched prior (rssm.py:186-193)
@@ -709,36 +769,10 @@ class Dreamer(nn.Module):
         ops.gemm(hN, W(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
         ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, ppin, m3, r3)
         ops.gemm(ppin, W(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
-        out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
 
-        # ---- image decoder (decoders.py:111-180): Linear, then deconv = GEMM + col2im gather (+bias+ELU)
-        dec = self.wm.decoder.image.model
-        x0 = b("dec.x0", N, 32 * cd)
-        ops.gemm(featN, W(dec[0].weight), x0, bias=self._raw(dec[0].bias), round_out=True)
-        dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
-        xin = x0
-        for li, (hi, ho, k, ci, co) in enumerate(dgeo):
-            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co)
-            ops.gemm(xin, self._decw[li], cols)
-            bias = self._raw(dec[2 + 2 * li].bias)
-            if li < 3:
-                a = b(f"dec.d{li}", N, ho, ho, co)
-                ops.col2im(cols, hi, hi, k, bias, ACT_ELU, a, round_out=True)
-                xin = a.view(N * ho * ho, co)
-            else:
-                image_dec, diff = b("dec.image", N, IC, 64, 64), b("dec.diff", N, IC, 64, 64)
-                l_img, csum = b("loss.img", N), b("dec.csum", N, IC)
-                ops.col2im_imgloss(cols, N, hi, hi, IC, k, bias, img, I, image_dec, diff, l_img, csum)
-
-        # ---- reward / terminal heads (decoders.py:257-319)
-        rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)
-        yr, yt = b("head.yr", N, 1), b("head.yt", N, 1)
-        self._mlp_fwd(rp, featN, yr, "rew", save=True)
-        self._mlp_fwd(tp, featN, yt, "term", save=True)
-        l_rew, dyr, rec_r = b("loss.rew", N), b("head.dyr", N, 1), b("head.rec_r", N)
-        l_term, dyt, rec_t = b("loss.term", N), b("head.dyt", N, 1), b("head.rec_t", N)
-        ops.scalar_head_loss(0, yr, obs["reward"].reshape(NB), I, l_rew, dyr, rec_r)
-        ops.scalar_head_loss(1, yt, obs["terminal"].reshape(NB), I, l_term, dyt, rec_t)
+        # ---- image decoder + reward / terminal heads on the posterior features
+        dd = self._decode_all(featN, img, obs, N, NB, I, "")
+        image_dec, l_img, l_rew, l_term, rec_r, rec_t = dd["image"], dd["l_img"], dd["l_rew"], dd["l_term"], dd["rec_r"], dd["rec_t"]
 
         # ---- KL + loss assembly (dreamer.py:328-379)
         l_kl, kl_exact = b("loss.kl", N), b("loss.klx", N)
@@ -760,7 +794,76 @@ class Dreamer(nn.Module):
         tensors = dict(loss_image=tbv[..., 1], image_rec=sel(image_dec), loss_reward=tbv[..., 2],
                        reward_rec=sel(rec_r), loss_terminal=tbv[..., 3], terminal_rec=sel(rec_t),
                        loss_kl=tbv[..., 4], entropy_prior=tbv[..., 5], entropy_post=tbv[..., 6])
+        if noise_image_pred is not None:
+            self._image_pred(obs, featN, prior, noise_image_pred, T, B, I, metrics, tensors)
         return dict(loss_model=means[0], out_state=out_state, metrics=metrics, tensors=tensors)
+
+    def _image_pred(self, obs, featN, prior, noise, T, B, I, metrics, tensors):
+        """dreamer.py:383-394: decode from a PRIOR sample (what the model predicts before seeing the observation);
+        reports the reconstruction losses as logprob_* and the decoded tensors as *_pred.  Logging branch."""
+        ops, d = self.ops, self.d
+        NB = T * B
+        N = NB * I
+        b = self._buf
+        featP = b("p.feat", N, d.F)
+        featP[:, :d.D].copy_(featN[:, :d.D])
+        ops.cat_sample(prior, noise, d.G, d.C, featP[:, d.D:])
+        img = obs["image"].reshape(NB, d.IC, 64, 64)
+        dd = self._decode_all(featP, img, obs, N, NB, I, "p.")
+        zeros = b("p.zeros", N, zero=True)
+        w, tb = b("p.loss.w", N), b("p.loss.tb", NB, 8)
+        ops.wm_loss(NB, I, 0.0, 1.0, 1.0, 1.0, dd["l_img"], dd["l_rew"], dd["l_term"], zeros, zeros, zeros, zeros, w, tb)
+        tbv = tb.view(T, B, 8)
+        sel = (lambda x: x.view(T, B, I, *x.shape[1:])[:, :, 0]) if I == 1 else \
+              (lambda x: x.view(T, B, I, *x.shape[1:]).mean(2))
+        lp_img, lp_rew, lp_term = tbv[..., 1], tbv[..., 2], tbv[..., 3]
+        nanmean = lambda x: torch.nansum(x) / (~torch.isnan(x)).sum()                # functions.py:150-151
+        extra_t = {}
+        for sig in (-1, 1):                                                          # decoders.py:96-101
+            m = torch.sign(obs["reward"]) == sig
+            extra_t[f"logprob_reward{sig}"] = lp_rew * m / m
+        m = obs["terminal"] > 0                                                      # decoders.py:103-106
+        extra_t["logprob_terminal1"] = lp_term * m / m
+        metrics.update(logprob_image=lp_img.mean(), logprob_reward=lp_rew.mean(), logprob_terminal=lp_term.mean(),
+                       **{k: nanmean(v) for k, v in extra_t.items()})
+        tensors.update(logprob_image=lp_img, logprob_reward=lp_rew, logprob_terminal=lp_term, **extra_t,
+                       image_pred=sel(dd["image"]), reward_pred=sel(dd["rec_r"]), terminal_pred=sel(dd["rec_t"]))
+
+    def _decode_all(self, featN, img, obs, N, NB, I, tag):
+        """MultiDecoder.training_step forward (decoders.py:50-108) on features (N,F): image decoder (Linear, then each
+        deconv = GEMM + col2im gather with bias+ELU; the last one fused with the image loss) and the reward / terminal
+        MLP heads with their losses.  Buffers are named `tag + ...` (tag "" = the training pass the backward reads)."""
+        ops, d = self.ops, self.d
+        cd, IC = d.cd, d.IC
+        b = lambda name, *shape, **kw: self._buf(tag + name, *shape, **kw)
+        W = self._w
+        dec = self.wm.decoder.image.model
+        x0 = b("dec.x0", N, 32 * cd)
+        ops.gemm(featN, W(dec[0].weight), x0, bias=self._raw(dec[0].bias), round_out=True)
+        dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
+        xin = x0
+        for li, (hi, ho, k, ci, co) in enumerate(dgeo):
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co)
+            ops.gemm(xin, self._decw[li], cols)
+            bias = self._raw(dec[2 + 2 * li].bias)
+            if li < 3:
+                a = b(f"dec.d{li}", N, ho, ho, co)
+                ops.col2im(cols, hi, hi, k, bias, ACT_ELU, a, round_out=True)
+                xin = a.view(N * ho * ho, co)
+            else:
+                image_dec, diff = b("dec.image", N, IC, 64, 64), b("dec.diff", N, IC, 64, 64)
+                l_img, csum = b("loss.img", N), b("dec.csum", N, IC)
+                ops.col2im_imgloss(cols, N, hi, hi, IC, k, bias, img, I, image_dec, diff, l_img, csum)
+        # reward / terminal heads (decoders.py:257-319)
+        rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)
+        yr, yt = b("head.yr", N, 1), b("head.yt", N, 1)
+        self._mlp_fwd(rp, featN, yr, tag + "rew", save=True)
+        self._mlp_fwd(tp, featN, yt, tag + "term", save=True)
+        l_rew, dyr, rec_r = b("loss.rew", N), b("head.dyr", N, 1), b("head.rec_r", N)
+        l_term, dyt, rec_t = b("loss.term", N), b("head.dyt", N, 1), b("head.rec_t", N)
+        ops.scalar_head_loss(0, yr, obs["reward"].reshape(NB), I, l_rew, dyr, rec_r)
+        ops.scalar_head_loss(1, yt, obs["terminal"].reshape(NB), I, l_term, dyt, rec_t)
+        return dict(image=image_dec, l_img=l_img, l_rew=l_rew, l_term=l_term, rec_r=rec_r, rec_t=rec_t)
 
     # ------------------------------------------------------------------ world model backward
     def _wm_backward(self, obs, T, B, I, H):
@@ -912,14 +1015,13 @@ class Dreamer(nn.Module):
                 da = da_prev
 
     # ------------------------------------------------------------------ imagination rollout
-    def _dream(self, T, B, I, H, noise_actor, noise_prior):
-        """dreamer.py:188-216: H x { actor -> sample action -> forward_prior }, forward only (reinforce)."""
+    def _dream(self, feats, N, H, noise_actor, noise_prior, tag):
+        """dreamer.py:188-216: H x { actor -> sample action -> forward_prior }, forward only (reinforce).
+        feats (H+1, N, F): feats[0] holds the start states; rows 1..H are written here."""
         ops, d, conf = self.ops, self.d, self.conf
-        N = T * B * I
-        b, W = self._buf, self._w
+        b, W = (lambda name, *shape, **kw: self._buf(tag + name, *shape, **kw)), self._w
         cell = self.wm.core.cell
         gru = cell.gru.layers[0]
-        feats = b("feats", H + 1, N, d.F)
         ap = self._mlp_params(self.ac.actor)
         alog = b("dream.alog", H, N, d.Aout)
         actions = b("dream.actions", H, N, d.A)
@@ -929,7 +1031,7 @@ class Dreamer(nn.Module):
         yp, pp, prior = b("dream.yp", N, d.Hd), b("dream.pp", N, d.Hd), b("dream.prior", N, d.Z)
         for i in range(H):
             f = feats[i]
-            self._mlp_fwd(ap, f, alog[i], "actor", rows_total=H * N, row0=i * N, save=True)
+            self._mlp_fwd(ap, f, alog[i], tag + "actor", rows_total=H * N, row0=i * N, save=True)
             if conf.actor_dist == "onehot":
                 ops.cat_sample(alog[i], noise_actor[i], 1, d.A, actions[i])
             else:
@@ -947,13 +1049,11 @@ class Dreamer(nn.Module):
             ops.cat_sample(prior, noise_prior[i], d.G, d.C, fn[:, d.D:])
 
     # ------------------------------------------------------------------ actor critic
-    def _actor_critic(self, T, B, I, H, want_grad):
+    def _actor_critic(self, feats, N, H, want_grad, tag):
         """a2c.py:61-149 on the dreamed features (all inputs detached, dreamer.py:153-157)."""
         ops, d, conf, ac = self.ops, self.d, self.conf, self.ac
-        N = T * B * I
         J = H + 1
-        b = self._buf
-        feats = b("feats", J, N, d.F)
+        b = lambda name, *shape, **kw: self._buf(tag + name, *shape, **kw)
         fall = feats.view(J * N, d.F)
         rp, tp = self._mlp_params(self.wm.decoder.reward.model), self._mlp_params(self.wm.decoder.terminal.model)
         cp, ctp, ap = self._mlp_params(ac.critic), self._mlp_params(ac.critic_target), self._mlp_params(ac.actor)
@@ -962,7 +1062,7 @@ class Dreamer(nn.Module):
         self._mlp_fwd(rp, fall, rew, "scratch")
         self._mlp_fwd(tp, fall, tlog, "scratch")
         self._mlp_fwd(ctp, fall, vt, "scratch")
-        self._mlp_fwd(cp, fall, v, "critic", save=True)
+        self._mlp_fwd(cp, fall, v, tag + "critic", save=True)
         term = b("ac.term", J, N)
         adv, agae, target = b("ac.adv", H, N), b("ac.agae", H, N), b("ac.target", H, N)
         weight, dv = b("ac.weight", H, N), b("ac.dv", H * N, 1)
@@ -978,8 +1078,8 @@ class Dreamer(nn.Module):
             ops.actor_loss_tanh_normal(conf.entropy, alog, actions, agae, weight, dal, sums[5:7])
         if want_grad:
             fH = fall[:H * N]
-            self._mlp_bwd(cp, fH, dv, "critic", rows_total=J * N)
-            self._mlp_bwd(ap, fH, dal, "actor", rows_total=H * N)
+            self._mlp_bwd(cp, fH, dv, tag + "critic", rows_total=J * N)
+            self._mlp_bwd(ap, fH, dal, tag + "actor", rows_total=H * N)
         hm = float(H * N)
         s = sums
         r_mean = s[3] / hm
@@ -989,8 +1089,52 @@ class Dreamer(nn.Module):
                        policy_value=f32(s[1] / float(N)), policy_value_im=f32(s[2] / hm), policy_reward=f32(r_mean),
                        policy_reward_std=f32(r_var.sqrt()))
         return dict(loss_actor=metrics["loss_actor"], loss_critic=metrics["loss_critic"], metrics=metrics,
-                    value=v.view(J, N), tensors=dict(value=v.view(J, N), value_target=target, value_advantage=adv,
-                                                     value_advantage_gae=agae, value_weight=weight))
+                    value=v.view(J, N), rew=rew.view(J, N), term=term,
+                    tensors=dict(value=v.view(J, N), value_target=target, value_advantage=adv,
+                                 value_advantage_gae=agae, value_weight=weight))
+
+    def _dream_for_log(self, obs, T, B, I, noise_actor, noise_prior):
+        """dreamer.py:165-180 (do_dream_tensors): dream T-1 steps from the first posterior state of every sequence, decode
+        the imagined images, evaluate the critic (log_only).  Logging branch, no gradients."""
+        ops, d = self.ops, self.d
+        Hl, BI = T - 1, B * I
+        N0 = T * B * I
+        feats0 = self._buf("feats", self.imag_horizon + 1, N0, d.F) if ("feats", (self.imag_horizon + 1, N0, d.F), torch.float32) in self._ws \
+            else next(v for k, v in self._ws.items() if k[0] == "feats" and k[1][1] == N0)
+        fl = self._buf("dl.feats", Hl + 1, B, d.F)
+        fl[0].copy_(feats0[0][0:BI:I])                                   # states[0, :, 0]
+        self._dream(fl, B, Hl, noise_actor, noise_prior, "dl.")
+        ac = self._actor_critic(fl, B, Hl, False, "dl.")
+        img = self._image_decode(fl.view((Hl + 1) * B, d.F), (Hl + 1) * B, "dl.")
+        actions = self._buf("dl.dream.actions", Hl, B, d.A)
+        t = ac["tensors"]
+        return dict(action_pred=torch.cat([obs["action"][:1], actions]), reward_pred=ac["rew"], terminal_pred=ac["term"],
+                    image_pred=img.view(T, B, d.IC, 64, 64), value=t["value"], value_target=t["value_target"],
+                    value_advantage=t["value_advantage"], value_advantage_gae=t["value_advantage_gae"],
+                    value_weight=t["value_weight"])
+
+    def _image_decode(self, featN, N, tag):
+        """ConvDecoder.forward (decoders.py:157-161) without a loss: (N,F) -> (N,C,64,64)."""
+        ops, d = self.ops, self.d
+        cd, IC = d.cd, d.IC
+        b = lambda name, *shape, **kw: self._buf(tag + name, *shape, **kw)
+        dec = self.wm.decoder.image.model
+        x0 = b("dec.x0", N, 32 * cd)
+        ops.gemm(featN, self._w(dec[0].weight), x0, bias=self._raw(dec[0].bias), round_out=True)
+        dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
+        xin = x0
+        for li, (hi, ho, k, ci, co) in enumerate(dgeo):
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co)
+            ops.gemm(xin, self._decw[li], cols)
+            bias = self._raw(dec[2 + 2 * li].bias)
+            if li < 3:
+                a = b(f"dec.d{li}", N, ho, ho, co)
+                ops.col2im(cols, hi, hi, k, bias, ACT_ELU, a, round_out=True)
+                xin = a.view(N * ho * ho, co)
+            else:
+                out = b("dec.image", N, IC, 64, 64)
+                ops.col2im(cols, hi, hi, k, bias, ACT_NONE, out.permute(0, 2, 3, 1), round_out=False)
+        return out
 
     def __str__(self):
         n = sum(p.numel() for p in self.parameters())

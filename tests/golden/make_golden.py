@@ -95,6 +95,48 @@ def run_case(name, spec):
     print(f"{name}: losses {fix['losses']}  oracle-vs-reference worst grad rel err {worst:.2e} -> {path}")
 
 
+def run_log_case(name, spec):
+    """Logging / evaluation branches of the reference (do_image_pred + do_dream_tensors, open-loop eval, inference):
+    the REFERENCE's outputs are the fixture; the module is checked against them in tests/test_dreamer_cpu.py and
+    tests/test_dreamer_gpu.py (there is no oracle restatement of these logging branches)."""
+    torch.distributions.Distribution.set_default_validate_args(False)
+    conf = make_conf(spec["preset"], device="cpu", **spec["over"])
+    T, B, I = conf.batch_length, conf.batch_size, conf.iwae_samples
+    torch.manual_seed(0)
+    ref = RefDreamer(conf)
+    ref.load_state_dict(seeded_state_dict(ref.state_dict(), WEIGHT_SEED))
+    obs = synthetic_batch(conf, seed=DATA_SEED)
+    g = torch.Generator().manual_seed(99)
+    state = (torch.tanh(torch.randn((B * I, conf.deter_dim), generator=g)), torch.zeros(B * I, conf.stoch_dim * conf.stoch_discrete))
+    sums = lambda d: {k: [float(v.double().nansum()), float(v.double().abs().nansum()), list(v.shape)] for k, v in d.items()}
+    torch.manual_seed(NOISE_SEED)
+    losses, out_state, metrics, tensors, dream = ref.training_step(obs, state, do_image_pred=True, do_dream_tensors=True)
+    fix = dict(case=name, preset=spec["preset"], overrides=spec["over"],
+               seeds=dict(noise=NOISE_SEED, data=DATA_SEED, weights=WEIGHT_SEED, state=99),
+               train_log=dict(losses=[float(l.detach().reshape(-1)[0]) for l in losses],
+                              metrics={k: float(v) for k, v in metrics.items()}, tensors=sums(tensors), dream=sums(dream)))
+    with torch.no_grad():
+        torch.manual_seed(NOISE_SEED)
+        l2, os2, m2, t2, _ = ref.training_step(obs, state, do_open_loop=True, do_image_pred=True)
+    fix["open_loop"] = dict(losses=[float(l.detach().reshape(-1)[0]) for l in l2], metrics={k: float(v) for k, v in m2.items()},
+                            tensors=sums(t2), out_state_h_sum=float(os2[0].double().sum()))
+    with torch.no_grad():
+        torch.manual_seed(NOISE_SEED)
+        o1 = {k: v[:1] for k, v in obs.items()}
+        dist, os3, m3 = ref.inference(o1, (state[0][:B], state[1][:B]))      # the actor path has no IWAE dimension
+    lg = dist.logits if conf.actor_dist == "onehot" else torch.cat([dist.base_dist.base_dist.loc, dist.base_dist.base_dist.scale], -1)
+    fix["inference"] = dict(dist_param_sum=float(lg.double().sum()), dist_param_abs=float(lg.double().abs().sum()),
+                            out_state_h_sum=float(os3[0].double().sum()), out_state_z_sum=float(os3[1].double().sum()),
+                            policy_value=float(m3["policy_value"]))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".json")
+    with open(path, "w") as f:
+        json.dump(fix, f, indent=1, sort_keys=True)
+    print(f"{name}: log/eval/inference fixture -> {path}")
+
+
 if __name__ == "__main__":
+    for n, sp in (("tiny_onehot_log", CASES["tiny_onehot"]), ("tiny_dmc_log", CASES["tiny_dmc"]),
+                  ("tiny_iwae3_log", CASES["tiny_iwae3"])):
+        run_log_case(n, sp)
     for n, s in CASES.items():
         run_case(n, s)

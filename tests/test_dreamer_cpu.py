@@ -109,4 +109,98 @@ def test_no_grad_mode_skips_backward_and_unsupported_configs_raise(ref_ops):
         with pytest.raises(NotImplementedError):
             Dreamer(make_conf("tiny", **bad))
     with pytest.raises(NotImplementedError):
-        model.training_step(obs, state, do_image_pred=True)
+        model.training_step(obs, state, do_open_loop=True)          # evaluation branch: only under no_grad
+
+
+LOG_CASES = ("tiny_onehot_log", "tiny_dmc_log", "tiny_iwae3_log")
+
+
+def check_sums(got, want, rtol=3e-4, what=""):
+    assert set(got) == set(want), (what, sorted(set(got) ^ set(want)))
+    for k, (sm, ab, shape) in want.items():
+        g = got[k].double()
+        assert list(g.shape) == shape, (what, k, list(g.shape), shape)
+        assert abs(float(g.abs().nansum()) - ab) <= rtol * max(ab, 1e-6) + 1e-5, (what, k, float(g.abs().nansum()), ab)
+        assert abs(float(g.nansum()) - sm) <= rtol * max(ab, 1e-6) + 1e-5, (what, k)
+
+
+def run_log_case(case, device="cpu"):
+    """Shared by the CPU (reference op table) and GPU (native kernels) tests."""
+    import torch
+    from oracle import dreamer_oracle as O
+    from tests.util import load_fixture
+    from pydreamer_b200.config import make_conf
+    from pydreamer_b200.replay import synthetic_batch
+    fx = load_fixture(case)
+    conf = make_conf(fx["preset"], device=str(device), **fx["overrides"])
+    T, B, I = conf.batch_length, conf.batch_size, conf.iwae_samples
+    mv = lambda d_: {k: v.to(device) for k, v in d_.items()}
+    obs = mv(synthetic_batch(conf, seed=fx["seeds"]["data"]))
+    g = torch.Generator().manual_seed(fx["seeds"]["state"])
+    state = (torch.tanh(torch.randn((B * I, conf.deter_dim), generator=g)).to(device),
+             torch.zeros(B * I, conf.stoch_dim * conf.stoch_discrete, device=device))
+    model = Dreamer(conf).to(device)
+    model.load_state_dict(seeded_weights(model.state_dict(), fx))
+    out = {}
+
+    def snap(x):      # returned metrics / tensors are views of the step workspace (valid until the next call): copy
+        if isinstance(x, torch.Tensor):
+            return x.detach().clone()
+        if isinstance(x, dict):
+            return {k: snap(v) for k, v in x.items()}
+        if isinstance(x, (tuple, list)):
+            return type(x)(snap(v) for v in x)
+        return x
+
+    torch.manual_seed(fx["seeds"]["noise"])
+    noise = mv(O.draw_noise(conf, T, B, image_pred=True, dream_log=True))
+    out["train_log"] = snap(model.training_step(obs, state, do_image_pred=True, do_dream_tensors=True, noise=noise))
+    with torch.no_grad():
+        torch.manual_seed(fx["seeds"]["noise"])
+        noise = mv(O.draw_noise(conf, T, B, image_pred=True))
+        out["open_loop"] = snap(model.training_step(obs, state, do_open_loop=True, do_image_pred=True, noise=noise))
+        torch.manual_seed(fx["seeds"]["noise"])
+        model._test_inference_noise = torch.empty(B * conf.stoch_dim, conf.stoch_discrete).exponential_().reshape(1, B, -1).to(device)
+        out["inference"] = model.inference({k: v[:1] for k, v in obs.items()}, (state[0][:B], state[1][:B]))
+    return fx, conf, out
+
+
+def _close(a, b, tol):
+    import math
+    return (math.isnan(a) and math.isnan(b)) or abs(a - b) <= tol * max(1.0, abs(b))
+
+
+def check_log_case(fx, conf, out, rtol):
+    losses, out_state, metrics, tensors, dream = out["train_log"]
+    w = fx["train_log"]
+    for a, b in zip(losses, w["losses"]):
+        assert abs(float(a.detach().reshape(-1)[0]) - b) <= rtol * max(1.0, abs(b))
+    assert set(metrics) == set(w["metrics"])
+    for k, v in w["metrics"].items():
+        assert _close(float(metrics[k]), v, 2 * rtol), k
+    check_sums(tensors, w["tensors"], rtol, "tensors")
+    check_sums(dream, w["dream"], rtol, "dream_tensors")
+    losses, out_state, metrics, tensors, _ = out["open_loop"]
+    w = fx["open_loop"]
+    for a, b in zip(losses, w["losses"]):
+        assert abs(float(a.detach().reshape(-1)[0]) - b) <= rtol * max(1.0, abs(b))
+    for k, v in w["metrics"].items():
+        assert _close(float(metrics[k]), v, 2 * rtol), k
+    check_sums(tensors, w["tensors"], rtol, "open-loop tensors")
+    assert abs(float(out_state[0].double().sum()) - w["out_state_h_sum"]) <= 1e-3
+    dist, os3, m3 = out["inference"]
+    w = fx["inference"]
+    import torch
+    lg = dist.logits if conf.actor_dist == "onehot" else torch.cat([dist.base_dist.base_dist.loc, dist.base_dist.base_dist.scale], -1)
+    assert abs(float(lg.double().abs().sum()) - w["dist_param_abs"]) <= rtol * w["dist_param_abs"]
+    assert abs(float(os3[0].double().sum()) - w["out_state_h_sum"]) <= 1e-3
+    assert abs(float(os3[1].double().sum()) - w["out_state_z_sum"]) <= 1e-6      # same sampled latent
+    assert abs(float(m3["policy_value"]) - w["policy_value"]) <= 2 * rtol * max(1.0, abs(w["policy_value"]))
+    a = dist.sample()
+    assert a.shape == (1, conf.batch_size, conf.action_dim) and torch.isfinite(dist.log_prob(a)).all()
+
+
+@pytest.mark.parametrize("case", LOG_CASES)
+def test_logging_eval_and_inference_branches_match_reference(ref_ops, case):
+    fx, conf, out = run_log_case(case)
+    check_log_case(fx, conf, out, 3e-4)

@@ -110,3 +110,12 @@ def test_optimizer_step_and_second_step_on_gpu():
         l.backward()
     torch.cuda.synchronize()
     assert all(torch.isfinite(l).all() for l in losses2)
+
+
+@pytest.mark.parametrize("case", ("tiny_onehot_log", "tiny_dmc_log", "tiny_iwae3_log"))
+def test_logging_eval_and_inference_branches_on_gpu(case):
+    """do_image_pred + do_dream_tensors, open-loop evaluation and inference() through the native kernels (tcgen05 TF32
+    product arm) against the reference's committed outputs.  Tolerance 2e-3 (TF32 operands; sums over tensors)."""
+    from tests.test_dreamer_cpu import check_log_case, run_log_case
+    fx, conf, out = run_log_case(case, DEV)
+    check_log_case(fx, conf, out, 2e-3)
