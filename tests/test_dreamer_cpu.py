@@ -187,13 +187,14 @@ def check_log_case(fx, conf, out, rtol):
     for k, v in w["metrics"].items():
         assert _close(float(metrics[k]), v, 2 * rtol), k
     check_sums(tensors, w["tensors"], rtol, "open-loop tensors")
-    assert abs(float(out_state[0].double().sum()) - w["out_state_h_sum"]) <= 1e-3
+    atol_h = 1e-3 if rtol < 1e-3 else 2e-2          # sum over B*D recurrent-state elements (TF32 arm: ~3e-4 each)
+    assert abs(float(out_state[0].double().sum()) - w["out_state_h_sum"]) <= atol_h
     dist, os3, m3 = out["inference"]
     w = fx["inference"]
     import torch
     lg = dist.logits if conf.actor_dist == "onehot" else torch.cat([dist.base_dist.base_dist.loc, dist.base_dist.base_dist.scale], -1)
     assert abs(float(lg.double().abs().sum()) - w["dist_param_abs"]) <= rtol * w["dist_param_abs"]
-    assert abs(float(os3[0].double().sum()) - w["out_state_h_sum"]) <= 1e-3
+    assert abs(float(os3[0].double().sum()) - w["out_state_h_sum"]) <= atol_h
     assert abs(float(os3[1].double().sum()) - w["out_state_z_sum"]) <= 1e-6      # same sampled latent
     assert abs(float(m3["policy_value"]) - w["policy_value"]) <= 2 * rtol * max(1.0, abs(w["policy_value"]))
     a = dist.sample()
