@@ -67,11 +67,22 @@ int pd_gemm(pd_handle* h, int M, int N, int K,
             const float* bias, const float* R, long ldr, int r_div,
             int act, int round_out, int accumulate, int flags, void* stream);
 
+/* Forward-only contraction with fp16 operands (tcgen05 kind::f16, fp32 accumulate / output): same 10-bit mantissa as
+ * TF32 at twice the tensor rate and half the operand bytes.  Used where no gradient flows through the GEMM (the
+ * imagination rollout and the heads evaluated on dreamed features, dreamer.py:188-216, a2c.py:88,112).
+ * A: [M][K] fp16, B: [N][K] fp16 (both K-major, ld % 8 == 0), C fp32. */
+int pd_gemm_f16(pd_handle* h, int M, int N, int K, const void* A, long lda, const void* B, long ldb,
+                float* C, long ldc, const float* bias, const float* R, long ldr, int r_div,
+                int act, int round_out, void* stream);
+/* dst(fp16)[m, n] = src(fp32)[m, n] */
+int pd_to_half(pd_handle* h, long M, long N, const float* src, long lds, void* dst, long ldd, void* stream);
+
 /* ---- LayerNorm(eps, biased var, affine) + ELU -------------------------------------------- */
 /* y = ELU(LN(x)); saves per-row mean / rstd.  common.py:45-51, rssm.py:105,110,115,139-140,144-145. */
 int pd_ln_elu_fwd(pd_handle* h, int M, int N, const float* x, long ldx,
                   const float* gamma, const float* beta, float eps,
-                  float* y, long ldy, float* mean, float* rstd, void* stream);
+                  float* y, long ldy, float* mean, float* rstd,
+                  void* y16 /* optional fp16 copy of y (operand of a forward-only pd_gemm_f16) */, long ldy16, void* stream);
 /* dx from dy; ACCUMULATES dgamma, dbeta and (optional) dbias (= column sums of dx, the grad of the
  * bias of the Linear that produced x) with atomics. */
 int pd_ln_elu_bwd(pd_handle* h, int M, int N, const float* dy, long lddy,
@@ -86,7 +97,7 @@ int pd_ln_elu_bwd(pd_handle* h, int M, int N, const float* dy, long lddy,
 int pd_gru_fwd(pd_handle* h, int M, int D, const float* gi, long ldgi, const float* gh, long ldgh,
                const float* hprev, long ldh, float* hout, long ldho,
                float* hmask, long ldhm, const float* mask_next,
-               float* gates, void* stream);
+               float* gates, void* h16 /* optional fp16 copy of h' */, long ldh16, void* stream);
 /* dh_out = dh_a + dh_b * mask_b (either optional);  outputs dgi[M,3D], dgh[M,3D] and dh_carry = dh_out*u. */
 int pd_gru_bwd(pd_handle* h, int M, int D, const float* dh_a, long ldda, const float* dh_b, long lddb,
                const float* mask_b, const float* gates, const float* hprev, long ldh,
@@ -100,7 +111,8 @@ int pd_gru_bwd(pd_handle* h, int M, int D, const float* dh_a, long ldda, const f
  * zmask (optional) = z * mask_next[m]; idx (optional) int32 [M,G]. */
 int pd_cat_sample(pd_handle* h, int M, int G, int C, const float* logits, long ldl,
                   const float* noise, long ldn, float* z, long ldz,
-                  float* zmask, long ldzm, const float* mask_next, int32_t* idx, void* stream);
+                  float* zmask, long ldzm, const float* mask_next, int32_t* idx,
+                  void* z16 /* optional fp16 copy of z */, long ldz16, void* stream);
 /* straight-through backward: dlogits = p * (dz - sum_c p dz) + alpha * rowscale[m] * extra;
  * dz = dz_a + dz_b * mask_b (each optional). */
 int pd_cat_st_bwd(pd_handle* h, int M, int G, int C, const float* logits, long ldl,

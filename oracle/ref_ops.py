@@ -65,13 +65,21 @@ class RefOps:
         return C
 
     # ------------------------------------------------------------------ rowwise
-    def ln_elu_fwd(self, x, gamma, beta, eps, y, mean, rstd):
+    def gemm_f16(self, A16, B16, C, *, bias=None, res=None, r_div=1, act=ACT_NONE, round_out=False):
+        return self.gemm(A16.to(C.dtype), B16.to(C.dtype), C, bias=bias, res=res, r_div=r_div, act=act)
+
+    def to_half(self, src, dst):
+        dst.copy_(src.to(dst.dtype))
+
+    def ln_elu_fwd(self, x, gamma, beta, eps, y, mean, rstd, y16=None):
         mu = x.mean(-1)
         var = x.var(-1, unbiased=False)
         r = 1.0 / torch.sqrt(var + eps)
         mean.copy_(mu)
         rstd.copy_(r)
         y.copy_(F.elu((x - mu[:, None]) * r[:, None] * gamma + beta))
+        if y16 is not None:
+            y16.copy_(y.to(y16.dtype))
 
     def ln_elu_bwd(self, dy, x, y, gamma, mean, rstd, dx, dgamma, dbeta, dbias=None):
         g = dy * _elu_grad_from_out(y)
@@ -86,7 +94,7 @@ class RefOps:
             dbias.add_(d.sum(0))
         dx.copy_(d)
 
-    def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None):
+    def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None, h16=None):
         D = hprev.shape[1]
         r = torch.sigmoid(gi[:, :D] + gh[:, :D])
         u = torch.sigmoid(gi[:, D:2 * D] + gh[:, D:2 * D])
@@ -96,6 +104,8 @@ class RefOps:
         if gates is not None:
             gates.view(-1, 4, D).copy_(torch.stack([r, u, n, ghn], 1))
         hout.copy_(hn)
+        if h16 is not None:
+            h16.copy_(hn.to(h16.dtype))
         if hmask is not None:
             hmask.copy_(hn * mask_next[:, None])
 
@@ -115,12 +125,14 @@ class RefOps:
         dgh.copy_(torch.cat([dr_pre, du_pre, dn_pre * r], 1))
         dh_carry.copy_(dh * u)
 
-    def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None):
+    def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]
         _, p = _group_softmax(logits, G, C)
         k = (p / noise.reshape(M, G, C)).argmax(-1)
         zz = F.one_hot(k, C).to(logits.dtype).reshape(M, G * C)
         z.copy_(zz)
+        if z16 is not None:
+            z16.copy_(zz.to(z16.dtype))
         if zmask is not None:
             zmask.copy_(zz * mask_next[:, None])
         if idx is not None:

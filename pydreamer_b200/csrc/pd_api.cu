@@ -2,8 +2,8 @@
 #include "pd_common.cuh"
 #include <stdlib.h>
 
-int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
-                           long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream);
+int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, long lda, int a_mn, const void* B,
+                           long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream, int f16);
 int pd_gemm_simt_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
                         long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream);
 
@@ -73,7 +73,18 @@ int pd_gemm(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_m
                         ((((uintptr_t)B) & 15) == 0) && N >= 8 && K >= 8;
     if (h->gemm_impl == PD_GEMM_SIMT || !tma_ok)
         return pd_gemm_simt_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream);
-    return pd_gemm_tcgen05_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream);
+    return pd_gemm_tcgen05_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream, 0);
+}
+
+int pd_gemm_f16(pd_handle* h, int M, int N, int K, const void* A, long lda, const void* B, long ldb, float* C, long ldc,
+                const float* bias, const float* R, long ldr, int r_div, int act, int round_out, void* stream) {
+    if (!h) return PD_ERR_ARG;
+    PD_REQUIRE(h, M > 0 && N >= 8 && K >= 8, "pd_gemm_f16: bad shape %d %d %d", M, N, K);
+    PD_REQUIRE(h, A && B && C, "pd_gemm_f16: null operand");
+    PdEpilogue e;
+    e.C = C; e.ldc = ldc; e.bias = bias; e.R = R; e.ldr = ldr; e.r_div = r_div > 0 ? r_div : 1;
+    e.act = act; e.round_out = round_out; e.accumulate = 0; e.c_zeroed = 0;
+    return pd_gemm_tcgen05_launch(h, M, N, K, A, lda, 0, B, ldb, 0, e, (cudaStream_t)stream, 1);
 }
 
 }  // extern "C"

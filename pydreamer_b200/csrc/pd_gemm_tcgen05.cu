@@ -39,6 +39,7 @@ struct GemmArgs {
     int a_mn, b_mn;
     int num_m, num_n, splits, kb_total, kb_per_split;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
+    int f16;                   // operands are fp16 (kind::f16, 64 elements per 128-byte k-block) instead of tf32
     int tma_store;             // C is TMA-addressable: epilogue uses cp.async.bulk.tensor store / reduce
     int extras_on_split0;      // split-K of a plain (non-accumulate) GEMM: split 0 adds bias/residual, C pre-zeroed
     PdEpilogue epi;
@@ -91,6 +92,15 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_c, uint64_t adesc, uin
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -174,7 +184,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    const int k0 = kb * BK;
+                    const int k0 = kb * (g.f16 ? 2 * BK : BK);
                     if (!g.a_mn) {
                         tma_load_2d(&tmA, &full[stage], sa, k0, m0);              // box {32 k, 128 m}
                     } else {
@@ -197,7 +207,8 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor (cute InstrDescriptor): c=F32, a=b=TF32, majors, N>>3, M>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) |
+            const uint32_t fmt = g.f16 ? 0u : 2u;                   // InstrDescriptor a/b format: 0 = F16, 2 = TF32
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)g.a_mn << 15) |
                                    ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
@@ -222,7 +233,8 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                                    : make_desc(sa + s * 32, 16, 1024, 2);
                         const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, g.mn_lbo, g.mn_sbo, 1)
                                                    : make_desc(sb + s * 32, 16, 1024, 2);
-                        tc_mma_tf32(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                        if (g.f16) tc_mma_f16(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                        else       tc_mma_tf32(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -405,6 +417,15 @@ __device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_c, uint64_t adesc,
         ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -467,7 +488,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     uint8_t* sb = sa + A_BYTES;
                     const uint32_t lbar = smem_u32(&full[stage]) & PEER_MASK;  // the leader's barrier collects both CTAs' bytes
                     if (leader) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
-                    const int k0 = kb * BK;
+                    const int k0 = kb * (g.f16 ? 2 * BK : BK);
                     if (!g.a_mn) {
                         tma_load_2d_2sm(&tmA, lbar, sa, k0, m0);
                     } else {
@@ -487,7 +508,8 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) |
+            const uint32_t fmt = g.f16 ? 0u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)g.a_mn << 15) |
                                    ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
@@ -509,7 +531,8 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                                    : make_desc(sa + s * 32, 16, 1024, 2);
                         const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, g.mn_lbo, g.mn_sbo, 1)
                                                    : make_desc(sb + s * 32, 16, 1024, 2);
-                        tc_mma_tf32_2sm(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                        if (g.f16) tc_mma_f16_2sm(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                        else       tc_mma_tf32_2sm(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                     }
                     tc_commit_2sm(&empty[stage]);      // frees the stage in BOTH CTAs
                     if (++stage == STAGES2) { stage = 0; phase ^= 1; }
@@ -621,13 +644,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D fp32 tensor map: dim0 = contiguous dimension.
-int make_map(pd_handle* h, CUtensorMap* tm, const float* base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems,
-             uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
+int make_map(pd_handle* h, CUtensorMap* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems,
+             uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz, int elt_bytes = 4) {
     cuuint64_t gdim[2] = {dim0, dim1};
-    cuuint64_t gstride[1] = {ld_elems * 4};
+    cuuint64_t gstride[1] = {ld_elems * (uint64_t)elt_bytes};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride,
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride,
                                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -638,8 +661,9 @@ int make_map(pd_handle* h, CUtensorMap* tm, const float* base, uint64_t dim0, ui
 
 }  // namespace
 
-int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
-                           long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream) {
+int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, long lda, int a_mn, const void* B,
+                           long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream, int f16) {
+    PD_REQUIRE(h, !f16 || (!a_mn && !b_mn && (lda % 8) == 0 && (ldb % 8) == 0), "pd_gemm_f16: K-major operands with ld %% 8 == 0 only");
     PD_REQUIRE(h, (lda % 4) == 0 && (ldb % 4) == 0, "pd_gemm(tcgen05): lda/ldb must be multiples of 4 (got %ld, %ld)",
                lda, ldb);
     PD_REQUIRE(h, (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "pd_gemm(tcgen05): A/B must be 16B aligned");
@@ -650,17 +674,20 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const float* A, lo
     }
     CUtensorMap tmA, tmB, tmC;
     int rc;
-    if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (f16)        rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 2 * BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, 2);
+    else if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     else       rc = make_map(h, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (!b_mn) rc = make_map(h, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (f16)        rc = make_map(h, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 2 * BK, BN, CU_TENSOR_MAP_SWIZZLE_128B, 2);
+    else if (!b_mn) rc = make_map(h, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
     else       rc = make_map(h, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
 
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.a_mn = a_mn; g.b_mn = b_mn;
     g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
-    g.kb_total = pd_cdiv(K, BK);
+    g.f16 = f16;
+    g.kb_total = pd_cdiv(K, f16 ? 2 * BK : BK);
     g.epi = epi;
     g.mn_lbo = 4096; g.mn_sbo = 512;
     if (const char* dbg = getenv("PD_GEMM_MN_DESC")) {   // bring-up aid: "lbo,sbo" in bytes

@@ -1,6 +1,7 @@
 // pd_misc.cu — small pointwise kernels, loss heads, world-model loss assembly, actor-critic
 // (GAE scan, actor/critic losses) and the fused optimizer.  All HBM- or latency-bound.
 #include "pd_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -43,6 +44,12 @@ __global__ void group_sum_kernel(long R, int I, int W, const float* __restrict__
         float acc = 0.f;
         for (int k = 0; k < I; ++k) acc += x[(row * I + k) * ldx + c];
         o[row * ldo + c] = pd_round_if(acc, r);
+    }
+}
+__global__ void to_half_kernel(long M, long N, const float* __restrict__ s, long lds, __half* __restrict__ d, long ldd) {
+    GRID_STRIDE(i, M * N) {
+        long m = i / N, c = i % N;
+        d[m * ldd + c] = __float2half_rn(s[m * lds + c]);
     }
 }
 __global__ void fill_kernel(float* x, long n, float v) { GRID_STRIDE(i, n) x[i] = v; }
@@ -388,6 +395,11 @@ int pd_colsum(pd_handle* h, long M, int N, const float* x, long ldx, float* out,
     dim3 grid((N + 31) / 32, (unsigned)gy);
     colsum_kernel<<<grid, block, 0, S(stream)>>>(M, N, x, ldx, out);
     PD_CHECK_LAUNCH(h, "colsum");
+    return PD_OK;
+}
+int pd_to_half(pd_handle* h, long M, long N, const float* src, long lds, void* dst, long ldd, void* stream) {
+    to_half_kernel<<<grid_for(M * N, 256, h->num_sms), 256, 0, S(stream)>>>(M, N, src, lds, (__half*)dst, ldd);
+    PD_CHECK_LAUNCH(h, "to_half");
     return PD_OK;
 }
 int pd_fill(pd_handle* h, float* x, long n, float v, void* stream) {

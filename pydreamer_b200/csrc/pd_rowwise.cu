@@ -4,6 +4,7 @@
 //   (or a 32-class group), lanes stride the contiguous dimension so every global access is a
 //   coalesced 128 B line, reductions are warp shuffles.
 #include "pd_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -12,7 +13,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(128)
 ln_elu_fwd_kernel(int M, int N, const float* __restrict__ x, long ldx, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, float* __restrict__ y, long ldy,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int round_out) {
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int round_out, __half* __restrict__ y16,
+                  long ldy16) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -40,8 +42,9 @@ ln_elu_fwd_kernel(int M, int N, const float* __restrict__ x, long ldx, const flo
     for (int i = 0; i < MAXV; ++i) {
         int c = lane + 32 * i;
         if (c < N) {
-            float t = (v[i] - mean) * rstd * gamma[c] + beta[c];
-            yr[c] = pd_round_if(pd_elu(t), round_out);
+            float t = pd_round_if(pd_elu((v[i] - mean) * rstd * gamma[c] + beta[c]), round_out);
+            yr[c] = t;
+            if (y16) y16[(long)row * ldy16 + c] = __float2half_rn(t);
         }
     }
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
@@ -118,7 +121,8 @@ ln_elu_bwd_kernel(int M, int N, const float* __restrict__ dy, long lddy, const f
 __global__ void __launch_bounds__(256)
 ln_elu_fwd_row_kernel(int N, const float* __restrict__ x, long ldx, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, float* __restrict__ y, long ldy,
-                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int round_out) {
+                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int round_out, __half* __restrict__ y16,
+                      long ldy16) {
     __shared__ float sh[33];
     const int row = blockIdx.x, t = threadIdx.x;
     const float* xr = x + (long)row * ldx;
@@ -134,7 +138,11 @@ ln_elu_fwd_row_kernel(int N, const float* __restrict__ x, long ldx, const float*
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int c = t + 256 * i;
-        if (c < N) yr[c] = pd_round_if(pd_elu((v[i] - mean) * rstd * gamma[c] + beta[c]), round_out);
+        if (c < N) {
+            float t = pd_round_if(pd_elu((v[i] - mean) * rstd * gamma[c] + beta[c]), round_out);
+            yr[c] = t;
+            if (y16) y16[(long)row * ldy16 + c] = __float2half_rn(t);
+        }
     }
     if (t == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
@@ -177,7 +185,7 @@ ln_elu_bwd_row_kernel(int N, const float* __restrict__ dy, long lddy, const floa
 __global__ void gru_fwd_kernel(int M, int D, const float* __restrict__ gi, long ldgi, const float* __restrict__ gh,
                                long ldgh, const float* __restrict__ hprev, long ldh, float* __restrict__ hout,
                                long ldho, float* __restrict__ hmask, long ldhm, const float* __restrict__ mask_next,
-                               float* __restrict__ gates, int round_out) {
+                               float* __restrict__ gates, int round_out, __half* __restrict__ h16, long ldh16) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)M * D) return;
     int m = (int)(idx / D), j = (int)(idx % D);
@@ -190,6 +198,7 @@ __global__ void gru_fwd_kernel(int M, int D, const float* __restrict__ gi, long 
     float hp = hprev[(long)m * ldh + j];
     float hn = pd_round_if((1.f - u) * n + u * hp, round_out);
     hout[(long)m * ldho + j] = hn;
+    if (h16) h16[(long)m * ldh16 + j] = __float2half_rn(hn);
     if (hmask) hmask[(long)m * ldhm + j] = hn * mask_next[m];
     if (gates) {
         float* g = gates + (long)m * 4 * D;
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(256)
 cat_sample_kernel(long groups, int G, int C, const float* __restrict__ logits, long ldl,
                   const float* __restrict__ noise, long ldn, float* __restrict__ z, long ldz,
                   float* __restrict__ zmask, long ldzm, const float* __restrict__ mask_next,
-                  int32_t* __restrict__ idx) {
+                  int32_t* __restrict__ idx, __half* __restrict__ z16, long ldz16) {
     const int lane = threadIdx.x & 31;
     long gid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (gid >= groups) return;
@@ -264,6 +273,7 @@ cat_sample_kernel(long groups, int G, int C, const float* __restrict__ logits, l
     if (valid) {
         float zz = (lane == k) ? 1.f : 0.f;
         z[m * ldz + (long)g * C + lane] = zz;
+        if (z16) z16[m * ldz16 + (long)g * C + lane] = __float2half_rn(zz);
         if (zmask) zmask[m * ldzm + (long)g * C + lane] = zz * mask_next[m];
     }
     if (idx && lane == 0) idx[m * G + g] = k;
@@ -349,17 +359,17 @@ __global__ void kl_kernel(int M, int G, int C, const float* __restrict__ post, l
 extern "C" {
 
 int pd_ln_elu_fwd(pd_handle* h, int M, int N, const float* x, long ldx, const float* gamma, const float* beta,
-                  float eps, float* y, long ldy, float* mean, float* rstd, void* stream) {
+                  float eps, float* y, long ldy, float* mean, float* rstd, void* y16, long ldy16, void* stream) {
     PD_REQUIRE(h, N >= 1 && N <= 1024, "pd_ln_elu_fwd: N=%d unsupported (1..1024)", N);
     cudaStream_t s = (cudaStream_t)stream;
     if (M <= 256) {
-        ln_elu_fwd_row_kernel<<<M, 256, 0, s>>>(N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops);
+        ln_elu_fwd_row_kernel<<<M, 256, 0, s>>>(N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops, (__half*)y16, ldy16);
         PD_CHECK_LAUNCH(h, "ln_elu_fwd_row");
         return PD_OK;
     }
     int grid = pd_cdiv(M, 4);
-    if (N <= 416) ln_elu_fwd_kernel<13><<<grid, 128, 0, s>>>(M, N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops);
-    else          ln_elu_fwd_kernel<32><<<grid, 128, 0, s>>>(M, N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops);
+    if (N <= 416) ln_elu_fwd_kernel<13><<<grid, 128, 0, s>>>(M, N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops, (__half*)y16, ldy16);
+    else          ln_elu_fwd_kernel<32><<<grid, 128, 0, s>>>(M, N, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, h->round_ops, (__half*)y16, ldy16);
     PD_CHECK_LAUNCH(h, "ln_elu_fwd");
     return PD_OK;
 }
@@ -386,11 +396,12 @@ int pd_ln_elu_bwd(pd_handle* h, int M, int N, const float* dy, long lddy, const 
 
 int pd_gru_fwd(pd_handle* h, int M, int D, const float* gi, long ldgi, const float* gh, long ldgh, const float* hprev,
                long ldh, float* hout, long ldho, float* hmask, long ldhm, const float* mask_next, float* gates,
-               void* stream) {
+               void* h16, long ldh16, void* stream) {
     PD_REQUIRE(h, !hmask || mask_next, "pd_gru_fwd: hmask needs mask_next");
     long n = (long)M * D;
     gru_fwd_kernel<<<pd_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(M, D, gi, ldgi, gh, ldgh, hprev, ldh, hout, ldho,
-                                                                    hmask, ldhm, mask_next, gates, h->round_ops);
+                                                                    hmask, ldhm, mask_next, gates, h->round_ops,
+                                                                    (__half*)h16, ldh16);
     PD_CHECK_LAUNCH(h, "gru_fwd");
     return PD_OK;
 }
@@ -407,12 +418,14 @@ int pd_gru_bwd(pd_handle* h, int M, int D, const float* dh_a, long ldda, const f
 }
 
 int pd_cat_sample(pd_handle* h, int M, int G, int C, const float* logits, long ldl, const float* noise, long ldn,
-                  float* z, long ldz, float* zmask, long ldzm, const float* mask_next, int32_t* idx, void* stream) {
+                  float* z, long ldz, float* zmask, long ldzm, const float* mask_next, int32_t* idx, void* z16, long ldz16,
+                  void* stream) {
     PD_REQUIRE(h, C >= 1 && C <= 32, "pd_cat_sample: C=%d unsupported (<=32)", C);
     PD_REQUIRE(h, !zmask || mask_next, "pd_cat_sample: zmask needs mask_next");
     long groups = (long)M * G;
     cat_sample_kernel<<<pd_cdiv(groups, 8), 256, 0, (cudaStream_t)stream>>>(groups, G, C, logits, ldl, noise, ldn, z, ldz,
-                                                                          zmask, ldzm, mask_next, idx);
+                                                                          zmask, ldzm, mask_next, idx, (__half*)z16,
+                                                                          ldz16);
     PD_CHECK_LAUNCH(h, "cat_sample");
     return PD_OK;
 }

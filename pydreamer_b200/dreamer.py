@@ -339,6 +339,7 @@ class Dreamer(nn.Module):
                     p.grad = garena[o:o + p.numel()].view(p.shape)
         self._arena, self._garena, self._arena_device = arena, garena, dev
         self._sarena = torch.zeros_like(arena)     # tf32-rounded shadow of the arena (GEMM operands)
+        self._harena = torch.zeros(arena.shape, dtype=torch.float16, device=dev)   # fp16 shadow (forward-only GEMMs)
         self._ws = {}
         self._graphs = {}
         self._ops = None
@@ -372,6 +373,9 @@ class Dreamer(nn.Module):
 
     # set False if the caller backwards with a non-unit grad_output (e.g. GradScaler with amp=True)
     _unit_grad_output = True
+    # forward-only layers (imagination rollout, heads on dreamed features) use fp16 tensor-core operands: the same
+    # 10-bit mantissa as TF32 at twice the MMA rate and half the operand traffic; no gradient flows through them.
+    fp16_forward = True
 
     # ------------------------------------------------------------------ reference API
     def init_optimizers(self, lr, lr_actor=None, lr_critic=None, eps=1e-5):
@@ -447,6 +451,9 @@ class Dreamer(nn.Module):
     def _w(self, p):      # rounded shadow (tensor-core operand)
         return self._view(self._sarena, p)
 
+    def _wh(self, p):     # fp16 shadow (operand of forward-only GEMMs)
+        return self._view(self._harena, p)
+
     def _raw(self, p):    # fp32 master (biases, LayerNorm affine)
         return self._view(self._arena, p)
 
@@ -464,6 +471,8 @@ class Dreamer(nn.Module):
             return
         ops = self.ops
         ops.round_copy(self._arena, self._sarena, True)
+        if self.fp16_forward:
+            ops.to_half(self._arena.view(1, -1), self._harena.view(1, -1))
         enc = self.wm.encoder.encoder_image.model
         self._encw = []
         for li, idx in enumerate((0, 2, 4, 6)):
@@ -492,13 +501,15 @@ class Dreamer(nn.Module):
                                out=seq[3 * L], hid=mlp.hidden_dim, out_dim=mlp.out_dim, in_dim=mlp.in_dim)
 
     # ------------------------------------------------------------------ MLP forward / backward
-    def _mlp_fwd(self, mp, x_in, out, tag, rows_total=None, row0=0, save=False):
+    def _mlp_fwd(self, mp, x_in, out, tag, rows_total=None, row0=0, save=False, x16=None):
         """out[rows, out_dim] = MLP(x_in).  With save=True the per-layer pre-norm x, post-ELU y and LN
-        statistics are kept in workspace buffers `tag` (rows_total rows, this call fills [row0, row0+rows))."""
+        statistics are kept in workspace buffers `tag` (rows_total rows, this call fills [row0, row0+rows)).
+        x16 (optional, fp16 copy of x_in): run the hidden-layer GEMMs with fp16 operands (forward-only use)."""
         ops = self.ops
         rows = x_in.shape[0]
         RT = rows_total or rows
-        inp = x_in
+        inp, inp16 = x_in, x16
+        f16 = x16 is not None
         for l in range(mp.L):
             if save:
                 x = self._buf(f"{tag}.x{l}", RT, mp.hid)[row0:row0 + rows]
@@ -510,10 +521,15 @@ class Dreamer(nn.Module):
                 y = self._buf(f"mlp.sy{l % 2}", rows, mp.hid)
                 mean = self._buf("mlp.sm", rows)
                 rstd = self._buf("mlp.sr", rows)
-            ops.gemm(inp, self._w(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
-            ops.ln_elu_fwd(x, self._raw(mp.ln[l].weight), self._raw(mp.ln[l].bias), 1e-3, y, mean, rstd)
-            inp = y
-        ops.gemm(inp, self._w(mp.out.weight), out, bias=self._raw(mp.out.bias))
+            if f16:
+                ops.gemm_f16(inp16, self._wh(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
+                y16 = self._buf(f"mlp.h16_{l % 2}", rows, mp.hid, dtype=torch.float16)
+            else:
+                ops.gemm(inp, self._w(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
+                y16 = None
+            ops.ln_elu_fwd(x, self._raw(mp.ln[l].weight), self._raw(mp.ln[l].bias), 1e-3, y, mean, rstd, y16)
+            inp, inp16 = y, y16
+        ops.gemm(inp, self._w(mp.out.weight), out, bias=self._raw(mp.out.bias))     # narrow output layer: fp32 operands
         return out
 
     def _mlp_bwd(self, mp, x_in, dout, tag, rows_total=None, din=None, din_accum=False):
@@ -1029,24 +1045,41 @@ class Dreamer(nn.Module):
         mm, rr = b("dream.m", N), b("dream.r", N)
         gi, gh = b("dream.gi", N, 3 * d.D), b("dream.gh", N, 3 * d.D)
         yp, pp, prior = b("dream.yp", N, d.Hd), b("dream.pp", N, d.Hd), b("dream.prior", N, d.Z)
+        f16 = self.fp16_forward
+        if f16:
+            f16b = b("feats16", H + 1, N, d.F, dtype=torch.float16)
+            ops.to_half(feats[0], f16b[0])
+            za16, pp16 = b("dream.za16", N, d.Hd, dtype=torch.float16), b("dream.pp16", N, d.Hd, dtype=torch.float16)
+            Wh = self._wh
         for i in range(H):
-            f = feats[i]
-            self._mlp_fwd(ap, f, alog[i], tag + "actor", rows_total=H * N, row0=i * N, save=True)
+            f, fn = feats[i], feats[i + 1]
+            fh, fnh = (f16b[i], f16b[i + 1]) if f16 else (None, None)
+            self._mlp_fwd(ap, f, alog[i], tag + "actor", rows_total=H * N, row0=i * N, save=True, x16=fh)
             if conf.actor_dist == "onehot":
                 ops.cat_sample(alog[i], noise_actor[i], 1, d.A, actions[i])
             else:
                 ops.tanh_normal_sample(alog[i], noise_actor[i], actions[i])
             ops.gemm(actions[i], W(cell.a_mlp.weight), aa)
-            ops.gemm(f[:, d.D:], W(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
-            ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr)
-            ops.gemm(za, W(gru.weight_ih), gi, bias=self._raw(gru.bias_ih))
-            ops.gemm(f[:, :d.D], W(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
-            fn = feats[i + 1]
-            ops.gru_fwd(gi, gh, f[:, :d.D], fn[:, :d.D])
-            ops.gemm(fn[:, :d.D], W(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
-            ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pp, mm, rr)
-            ops.gemm(pp, W(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
-            ops.cat_sample(prior, noise_prior[i], d.G, d.C, fn[:, d.D:])
+            if f16:
+                ops.gemm_f16(fh[:, d.D:], Wh(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
+                ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr, za16)
+                ops.gemm_f16(za16, Wh(gru.weight_ih), gi, bias=self._raw(gru.bias_ih))
+                ops.gemm_f16(fh[:, :d.D], Wh(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+                ops.gru_fwd(gi, gh, f[:, :d.D], fn[:, :d.D], h16=fnh[:, :d.D])
+                ops.gemm_f16(fnh[:, :d.D], Wh(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
+                ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pp, mm, rr, pp16)
+                ops.gemm_f16(pp16, Wh(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
+                ops.cat_sample(prior, noise_prior[i], d.G, d.C, fn[:, d.D:], z16=fnh[:, d.D:])
+            else:
+                ops.gemm(f[:, d.D:], W(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
+                ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr)
+                ops.gemm(za, W(gru.weight_ih), gi, bias=self._raw(gru.bias_ih))
+                ops.gemm(f[:, :d.D], W(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+                ops.gru_fwd(gi, gh, f[:, :d.D], fn[:, :d.D])
+                ops.gemm(fn[:, :d.D], W(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
+                ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pp, mm, rr)
+                ops.gemm(pp, W(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
+                ops.cat_sample(prior, noise_prior[i], d.G, d.C, fn[:, d.D:])
 
     # ------------------------------------------------------------------ actor critic
     def _actor_critic(self, feats, N, H, want_grad, tag):
@@ -1059,10 +1092,11 @@ class Dreamer(nn.Module):
         cp, ctp, ap = self._mlp_params(ac.critic), self._mlp_params(ac.critic_target), self._mlp_params(ac.actor)
         rew, tlog = b("ac.rew", J * N, 1), b("ac.tlog", J * N, 1)
         vt, v = b("ac.vt", J * N, 1), b("ac.v", J * N, 1)
-        self._mlp_fwd(rp, fall, rew, "scratch")
-        self._mlp_fwd(tp, fall, tlog, "scratch")
-        self._mlp_fwd(ctp, fall, vt, "scratch")
-        self._mlp_fwd(cp, fall, v, tag + "critic", save=True)
+        fall16 = b("feats16", J, N, d.F, dtype=torch.float16).view(J * N, d.F) if self.fp16_forward else None
+        self._mlp_fwd(rp, fall, rew, "scratch", x16=fall16)
+        self._mlp_fwd(tp, fall, tlog, "scratch", x16=fall16)
+        self._mlp_fwd(ctp, fall, vt, "scratch", x16=fall16)
+        self._mlp_fwd(cp, fall, v, tag + "critic", save=True, x16=fall16)
         term = b("ac.term", J, N)
         adv, agae, target = b("ac.adv", H, N), b("ac.agae", H, N), b("ac.target", H, N)
         weight, dv = b("ac.weight", H, N), b("ac.dv", H * N, 1)

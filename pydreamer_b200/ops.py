@@ -92,11 +92,27 @@ class NativeOps:
             prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), int(accumulate))))
         return C
 
+    def gemm_f16(self, A16, B16, C, *, bias=None, res=None, r_div=1, act=ACT_NONE, round_out=False):
+        """C[M,N] (fp32) = A16[M,K] B16[N,K]^T with fp16 operands (forward-only layers)."""
+        M, N = C.shape
+        K = A16.shape[1]
+        assert A16.dtype == torch.float16 and B16.dtype == torch.float16 and B16.shape == (N, K) and A16.shape[0] == M
+        rc = self.lib.pd_gemm_f16(self.h, M, N, K, _ptr(A16), _ld(A16), _ptr(B16), _ld(B16), _ptr(C), _ld(C), _ptr(bias),
+                                  _ptr(res), _ld(res) if res is not None else 0, int(r_div), int(act), int(round_out),
+                                  self._s())
+        self._ck(rc, "pd_gemm_f16")
+        return C
+
+    def to_half(self, src, dst):
+        M, N = src.shape
+        self._ck(self.lib.pd_to_half(self.h, M, N, _ptr(src), _ld(src), _ptr(dst), _ld(dst), self._s()), "pd_to_half")
+
     # ------------------------------------------------------------------ rowwise
-    def ln_elu_fwd(self, x, gamma, beta, eps, y, mean, rstd):
+    def ln_elu_fwd(self, x, gamma, beta, eps, y, mean, rstd, y16=None):
         M, N = x.shape
         self._ck(self.lib.pd_ln_elu_fwd(self.h, M, N, _ptr(x), _ld(x), _ptr(gamma), _ptr(beta), float(eps),
-                                        _ptr(y), _ld(y), _ptr(mean), _ptr(rstd), self._s()), "pd_ln_elu_fwd")
+                                        _ptr(y), _ld(y), _ptr(mean), _ptr(rstd), _ptr(y16),
+                                        _ld(y16) if y16 is not None else 0, self._s()), "pd_ln_elu_fwd")
 
     def ln_elu_bwd(self, dy, x, y, gamma, mean, rstd, dx, dgamma, dbeta, dbias=None):
         M, N = x.shape
@@ -104,11 +120,12 @@ class NativeOps:
                                         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ld(dx), _ptr(dgamma),
                                         _ptr(dbeta), _ptr(dbias), self._s()), "pd_ln_elu_bwd")
 
-    def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None):
+    def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None, h16=None):
         M, D = hprev.shape
         self._ck(self.lib.pd_gru_fwd(self.h, M, D, _ptr(gi), _ld(gi), _ptr(gh), _ld(gh), _ptr(hprev), _ld(hprev),
                                      _ptr(hout), _ld(hout), _ptr(hmask), _ld(hmask) if hmask is not None else 0,
-                                     _ptr(mask_next), _ptr(gates), self._s()), "pd_gru_fwd")
+                                     _ptr(mask_next), _ptr(gates), _ptr(h16), _ld(h16) if h16 is not None else 0,
+                                     self._s()), "pd_gru_fwd")
 
     def gru_bwd(self, dh_a, dh_b, mask_b, gates, hprev, dgi, dgh, dh_carry):
         M, D = hprev.shape
@@ -117,11 +134,12 @@ class NativeOps:
                                      _ld(hprev), _ptr(dgi), _ld(dgi), _ptr(dgh), _ld(dgh), _ptr(dh_carry),
                                      _ld(dh_carry), self._s()), "pd_gru_bwd")
 
-    def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None):
+    def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]
         self._ck(self.lib.pd_cat_sample(self.h, M, G, C, _ptr(logits), _ld(logits), _ptr(noise), _ld(noise), _ptr(z),
                                         _ld(z), _ptr(zmask), _ld(zmask) if zmask is not None else 0, _ptr(mask_next),
-                                        _ptr(idx), self._s()), "pd_cat_sample")
+                                        _ptr(idx), _ptr(z16), _ld(z16) if z16 is not None else 0, self._s()),
+                 "pd_cat_sample")
 
     def cat_st_bwd(self, logits, G, C, dz_a, dz_b, mask_b, extra, rowscale, alpha, dlogits):
         M = logits.shape[0]

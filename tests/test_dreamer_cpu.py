@@ -20,9 +20,10 @@ def ref_ops():
     pd_ops.set_ops_for_testing(None)
 
 
-def run_model(case):
+def run_model(case, fp16_forward=False):
     fx, conf, obs, state, noise = build_case(case)
     model = Dreamer(conf)
+    model.fp16_forward = fp16_forward
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
     losses, out_state, metrics, tensors, dream = model.training_step(obs, state, noise=noise)
@@ -60,6 +61,18 @@ def test_training_step_matches_reference_golden(ref_ops, case):
         assert abs(float(g.double().sum()) - fx["grad_sums"][k]) <= 5e-4 * max(want, 1e-6) * g.numel() ** 0.5 + 1e-8, k
     assert not out_state[0].requires_grad and abs(float(out_state[0].double().sum()) - fx["out_state_h_sum"]) < 1e-3
     assert all(p.grad is None for p in model.ac.critic_target.parameters())
+
+
+def test_fp16_forward_plumbing_stays_within_tolerance(ref_ops):
+    """Imagination rollout / dreamed-feature heads with fp16 GEMM operands (forward-only layers): same schedule, fp16
+    copies of activations and weights; the posterior samples are untouched, actor/critic losses move by < 2e-3."""
+    fx, conf, model, opts, losses, out_state, metrics, tensors = run_model("tiny_onehot", fp16_forward=True)
+    for i, (got, want) in enumerate(zip(losses, fx["losses"])):
+        assert abs(float(got.detach().reshape(-1)[0]) - want) <= (5e-5 if i < 2 else 5e-3) * max(1.0, abs(want)), (i, got, want)
+    named = dict(model.named_parameters())
+    for k, want in fx["grad_norms"].items():
+        if k.startswith("wm."):                       # world-model gradients do not depend on the dream
+            assert abs(float(named[k].grad.double().norm()) - want) <= 2e-4 * max(want, 1e-6) + 1e-9, k
 
 
 def test_state_dict_roundtrip_and_grad_clip_and_optimizer(ref_ops):
@@ -140,6 +153,7 @@ def run_log_case(case, device="cpu"):
     state = (torch.tanh(torch.randn((B * I, conf.deter_dim), generator=g)).to(device),
              torch.zeros(B * I, conf.stoch_dim * conf.stoch_discrete, device=device))
     model = Dreamer(conf).to(device)
+    model.fp16_forward = str(device) != "cpu"
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     out = {}
 

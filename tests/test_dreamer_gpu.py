@@ -22,6 +22,7 @@ def run_gpu(case, impl, rounding):
     fx, conf, obs, state, noise = build_case(case, DEV)
     model = Dreamer(conf).to(DEV)
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
+    model.fp16_forward = (impl == 0)          # the exact arm keeps every GEMM in fp32
     model._ensure_arena()
     model.ops.set_gemm_impl(impl)
     model.ops.set_round_operands(rounding)

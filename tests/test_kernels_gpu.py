@@ -417,3 +417,44 @@ def test_optimizer_kernels_against_torch_adamw(ops):
         ops.inc(step)
         ops.adamw(p, gc, m, v, 3e-4, 0.9, 0.999, 1e-5, 0.01, step)
     close(p, pt.detach(), 1e-5, 1e-6, "adamw params after 3 steps")
+
+
+@pytest.mark.parametrize("M,N,K", [(50, 1000, 1024), (2500, 400, 3072), (2500, 6144, 1000), (640, 1000, 1000), (128, 128, 64)])
+def test_gemm_f16_operands_exact_on_integers(ops, ref, M, N, K):
+    """kind::f16 path (forward-only layers): integer operands are exact in fp16, fp32 accumulation is exact."""
+    if DEV == "cpu":
+        pytest.skip("dry run")
+    ops.set_gemm_impl(0)
+    A, B = ints(M, K, seed=1), ints(N, K, seed=2)
+    bias, res = ints(N, seed=3), ints(M, N, seed=4)
+    C, Cr = torch.full((M, N), float("nan"), device=DEV), torch.empty(M, N, device=DEV)
+    ops.gemm_f16(A.half(), B.half(), C, bias=bias, res=res)
+    ref.gemm(A, B, Cr, bias=bias, res=res)
+    assert torch.equal(C, Cr), f"max diff {(C - Cr).abs().max().item()}"
+    big = torch.zeros(M, K + 64, device=DEV, dtype=torch.float16)
+    big[:, 8:8 + K] = A.half()
+    ops.gemm_f16(big[:, 8:8 + K], B.half(), C, act=1)                  # strided fp16 view + ELU epilogue
+    ref.gemm(A, B, Cr, act=1)
+    close(C, Cr, 1e-6, 1e-6, "f16 strided")
+
+
+def test_fp16_side_outputs_of_producers(ops, ref):
+    if DEV == "cpu":
+        pytest.skip("dry run")
+    M, N, D, G, C = 300, 1000, 256, 32, 32
+    x, gamma, beta = rnd(M, N, scale=2.0), rnd(N) * 0.5 + 1, rnd(N, seed=3) * 0.1
+    y, mean, rstd = torch.empty(M, N, device=DEV), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    y16 = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    ops.ln_elu_fwd(x, gamma, beta, 1e-3, y, mean, rstd, y16)
+    assert torch.equal(y16, y.half())
+    gi, gh, hp = rnd(M, 3 * D), rnd(M, 3 * D, seed=1), torch.tanh(rnd(M, D, seed=2))
+    hout, h16 = torch.empty(M, D, device=DEV), torch.empty(M, D, device=DEV, dtype=torch.float16)
+    ops.gru_fwd(gi, gh, hp, hout, h16=h16)
+    assert torch.equal(h16, hout.half())
+    logits, noise = rnd(M, G * C, scale=2.0), torch.empty(M, G * C, device=DEV).exponential_()
+    z, z16 = torch.empty(M, G * C, device=DEV), torch.empty(M, G * C, device=DEV, dtype=torch.float16)
+    ops.cat_sample(logits, noise, G, C, z, z16=z16)
+    assert torch.equal(z16, z.half())
+    src, dst = rnd(77, 130), torch.empty(77, 130, device=DEV, dtype=torch.float16)
+    ops.to_half(src, dst)
+    assert torch.equal(dst, src.half())

@@ -57,6 +57,7 @@ def _worker(rank, port, out):
     conf, obs, noise = _inputs()
     lconf = make_conf("tiny", device="cpu", batch_size=BG // WORLD)
     model = Dreamer(lconf)
+    model.fp16_forward = False
     if rank == 0:
         model.load_state_dict(seeded_state_dict(model.state_dict(), 3))
     model._dp = GradAllReduce(WORLD)
@@ -77,6 +78,7 @@ def test_two_rank_gloo_matches_single_process_global_batch(tmp_path):
     try:
         conf, obs, noise = _inputs()
         model = Dreamer(conf)
+        model.fp16_forward = False
         model.load_state_dict(seeded_state_dict(model.state_dict(), 3))
         norms = _run(model, conf, obs, noise, BG)
     finally:
