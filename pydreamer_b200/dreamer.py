@@ -312,7 +312,7 @@ class Dreamer(nn.Module):
             start = off
             for p in self._group_params[gname]:
                 self._offsets[id(p)] = off
-                off += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned (TMA)
+                off += (p.numel() + 7) // 8 * 8          # every tensor 16-byte aligned in the fp32 AND the fp16 arena (TMA)
             self._group_range[gname] = (start, off)
         self._arena_numel = off
         self._train_numel = self._group_range["critic"][1]
