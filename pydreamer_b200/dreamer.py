@@ -375,7 +375,7 @@ class Dreamer(nn.Module):
     _unit_grad_output = True
     # forward-only layers (imagination rollout, heads on dreamed features) use fp16 tensor-core operands: the same
     # 10-bit mantissa as TF32 at twice the MMA rate and half the operand traffic; no gradient flows through them.
-    fp16_forward = True
+    fp16_forward = os.environ.get("PD_B200_FP16_FORWARD", "1") != "0"
 
     # ------------------------------------------------------------------ reference API
     def init_optimizers(self, lr, lr_actor=None, lr_critic=None, eps=1e-5):

@@ -8,7 +8,7 @@ from pydreamer_b200.ops import NativeOps
 def main():
     reps = 20
     shapes = []
-    args = [a for a in sys.argv[1:] if a != '--chain']
+    args = [a for a in sys.argv[1:] if a not in ('--chain', '--f16')]
     if "--reps" in args:
         i = args.index("--reps"); reps = int(args[i + 1]); del args[i:i + 2]
     for a in args:
@@ -48,8 +48,14 @@ def main():
         bv = torch.randn(N, device="cuda") if bias else None
         rv = torch.randn(M, N, device="cuda") if res else None
         flush = torch.empty(64 * 1024 * 1024, device="cuda")
+        f16 = "--f16" in sys.argv
+        if f16:
+            A16, B16 = A.half(), B.half()
         def run():
-            ops.gemm(A, B, C, a_mn=bool(a_mn), b_mn=bool(b_mn), accumulate=bool(acc), bias=bv, res=rv)
+            if f16:
+                ops.gemm_f16(A16, B16, C, bias=bv, res=rv)
+            else:
+                ops.gemm(A, B, C, a_mn=bool(a_mn), b_mn=bool(b_mn), accumulate=bool(acc), bias=bv, res=rv)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
