@@ -59,22 +59,43 @@ __global__ void im2col_planar_kernel(long total, int Hout, int Wout, int Cc, int
 }
 
 // NHWC fast path: one thread moves 4 consecutive channels (16 B) of one tap.
-__global__ void im2col_v4_kernel(long total4, int Hout, int Wout, int C4, int k, const float* __restrict__ in,
-                                 long sN, long sY, long sX, float* __restrict__ col, long ldcol, int round_out) {
+__global__ void __launch_bounds__(256)
+im2col_v4_kernel(long total4, int Hout, int Wout, int C4, int k, const float* __restrict__ in,
+                 long sN, long sY, long sX, float* __restrict__ col, long ldcol, int round_out) {
+    // 4 independent 16-byte moves per thread per iteration (loads issued before the stores) keep enough bytes in flight
+    // to approach HBM bandwidth; consecutive threads take consecutive 16-byte chunks.
     const int KK4 = k * k * C4;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
-        long row = idx / KK4;
-        int kidx = (int)(idx % KK4);
-        int c4 = kidx % C4;
-        int r = kidx / C4;
-        int kw = r % k, kh = r / k;
-        int ox = (int)(row % Wout);
-        long t = row / Wout;
-        int oy = (int)(t % Hout);
-        long n = t / Hout;
-        float4 v = *reinterpret_cast<const float4*>(in + n * sN + (long)(2 * oy + kh) * sY + (long)(2 * ox + kw) * sX + c4 * 4);
-        if (round_out) { v.x = pd_tf32(v.x); v.y = pd_tf32(v.y); v.z = pd_tf32(v.z); v.w = pd_tf32(v.w); }
-        *reinterpret_cast<float4*>(col + row * ldcol + (long)kidx * 4) = v;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long base = (long)blockIdx.x * blockDim.x + threadIdx.x; base < total4; base += 4 * stride) {
+        float4 v[4];
+        long dsto[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long idx = base + u * stride;
+            dsto[u] = -1;
+            if (idx < total4) {
+                long row = idx / KK4;
+                int kidx = (int)(idx - row * KK4);
+                int c4 = kidx % C4;
+                int r = kidx / C4;
+                int kw = r % k, kh = r / k;
+                int ox = (int)(row % Wout);
+                long t = row / Wout;
+                int oy = (int)(t % Hout);
+                long n = t / Hout;
+                v[u] = __ldg(reinterpret_cast<const float4*>(in + n * sN + (long)(2 * oy + kh) * sY +
+                                                             (long)(2 * ox + kw) * sX + c4 * 4));
+                dsto[u] = row * ldcol + (long)kidx * 4;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (dsto[u] >= 0) {
+                float4 w = v[u];
+                if (round_out) { w.x = pd_tf32(w.x); w.y = pd_tf32(w.y); w.z = pd_tf32(w.z); w.w = pd_tf32(w.w); }
+                *reinterpret_cast<float4*>(col + dsto[u]) = w;
+            }
+        }
     }
 }
 
@@ -90,19 +111,24 @@ __global__ void col2im_v4_kernel(long total4, int Hin, int Win, int Hout, int Wo
         int y = (int)(t % Hout);
         long n = t / Hout;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kh = y & 1; kh < k; kh += 2) {
-            int iy = (y - kh) >> 1;
-            if (iy < 0) break;
-            if (iy >= Hin) continue;
-            for (int kw = x & 1; kw < k; kw += 2) {
-                int ix = (x - kw) >> 1;
-                if (ix < 0) break;
-                if (ix >= Win) continue;
-                const float4 v = *reinterpret_cast<const float4*>(col + ((n * Hin + iy) * Win + ix) * ldcol +
-                                                                   (long)(kh * k + kw) * Cc + c4 * 4);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        float4 tap[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int kh = (y & 1) + 2 * a;
+            const int iy = (y - kh) >> 1;
+            const bool oky = kh < k && iy >= 0 && iy < Hin;
+#pragma unroll
+            for (int bq = 0; bq < 3; ++bq) {
+                const int kw = (x & 1) + 2 * bq;
+                const int ix = (x - kw) >> 1;
+                tap[a * 3 + bq] = (oky && kw < k && ix >= 0 && ix < Win)
+                    ? __ldg(reinterpret_cast<const float4*>(col + ((n * Hin + iy) * Win + ix) * ldcol +
+                                                            (long)(kh * k + kw) * Cc + c4 * 4))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { acc.x += tap[i].x; acc.y += tap[i].y; acc.z += tap[i].z; acc.w += tap[i].w; }
         if (bias) {
             const float4 b = *reinterpret_cast<const float4*>(bias + c4 * 4);
             acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
@@ -239,7 +265,7 @@ int pd_im2col(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, int korder,
     const bool v4 = korder == 0 && sC == 1 && (Cc % 4) == 0 && (sN % 4) == 0 && (sY % 4) == 0 && (sX % 4) == 0 &&
                     (ldcol % 4) == 0 && ((((uintptr_t)in) | ((uintptr_t)col)) & 15) == 0;
     if (v4) {
-        im2col_v4_kernel<<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        im2col_v4_kernel<<<grid_for(total / 16 + 1, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
             total / 4, Hout, Wout, Cc / 4, k, in, sN, sY, sX, col, ldcol, round_out && h->round_ops);
         PD_CHECK_LAUNCH(h, "im2col_v4");
         return PD_OK;
