@@ -70,7 +70,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -358,8 +358,9 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     line = dict(
         metric="grad_steps_per_sec", value=steps_per_s, unit="steps/s", n_gpus=world, steps=args.steps,
+        global_steps_per_sec=steps_per_s / world,
         warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
-        vs_baseline=None, dtype="tf32 (fp32 storage, fp32 accumulate)", data="synthetic",
+        vs_baseline=None, dtype="tf32 (fp32 storage + accumulate); fp16 operands on forward-only layers" if model.fp16_forward else "tf32 (fp32 storage + accumulate)", data="synthetic",
         imagined_samples_per_sec=steps_per_s * per_step_samples,
         config=dict(workload=f"{args.config}: Dreamer.training_step+4x backward+grad_clip+4x AdamW, per-GPU B={B} T={T} H={H} "
                              f"I={I} deter={conf.deter_dim} stoch={conf.stoch_dim}x{conf.stoch_discrete} image 64x64x3",
@@ -374,7 +375,10 @@ def run_ours(args):
         roofline=dict(bound="tensor", kernel="pd_gemm_tf32_kernel (tcgen05.mma kind::tf32)", achieved=achieved,
                       peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"],
                       peak_source=pk["source"] + ": cuBLAS bf16 sustained; tf32 nominal peak is half of bf16",
-                      traffic=None, gemm_launches_per_step=len(prof), gemm_ms_per_step=gemm_ms,
+                      traffic=171.3e6 if args.config == "atari" else None,
+                      traffic_note="dram read+write of the largest TF32 launch (2500x6144x2048, 2-CTA kernel) from "
+                                   "profiles/r01_c_gemm_2cta_2500x6144x2048_full.ncu-rep; its algorithmic bytes are 132 MB",
+                      gemm_launches_per_step=len(prof), gemm_ms_per_step=gemm_ms,
                       gemm_share_of_step=gemm_ms / (ms / args.steps), gemm_flops_per_step=gemm_flops,
                       step_algorithmic_tflop=ALGO_FLOPS_ATARI / 1e12 if args.config == "atari" else None,
                       step_tflops=(ALGO_FLOPS_ATARI / 1e12) / (ms / args.steps / 1000.0) if args.config == "atari" else None),

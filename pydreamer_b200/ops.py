@@ -97,10 +97,17 @@ class NativeOps:
         M, N = C.shape
         K = A16.shape[1]
         assert A16.dtype == torch.float16 and B16.dtype == torch.float16 and B16.shape == (N, K) and A16.shape[0] == M
+        prof = self.gemm_profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = self.lib.pd_gemm_f16(self.h, M, N, K, _ptr(A16), _ld(A16), _ptr(B16), _ld(B16), _ptr(C), _ld(C), _ptr(bias),
                                   _ptr(res), _ld(res) if res is not None else 0, int(r_div), int(act), int(round_out),
                                   self._s())
         self._ck(rc, "pd_gemm_f16")
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, "f16", 0, 0)))
         return C
 
     def to_half(self, src, dst):
