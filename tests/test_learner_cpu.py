@@ -1,0 +1,58 @@
+"""Learner step + checkpoint format on CPU with the reference op table; when a reference checkout /
+install is reachable the checkpoint is also loaded, strict, into the UNMODIFIED reference Dreamer."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle.ref_ops import RefOps
+from pydreamer_b200 import ops as pd_ops
+from pydreamer_b200.config import make_conf
+from pydreamer_b200.learner import Learner
+from pydreamer_b200.replay import synthetic_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def ref_ops():
+    pd_ops.set_ops_for_testing(RefOps("cpu"))
+    yield
+    pd_ops.set_ops_for_testing(None)
+
+
+def test_learner_steps_carry_state_and_checkpoint_roundtrip(ref_ops, tmp_path):
+    conf = make_conf("tiny", device="cpu")
+    lr = Learner(conf, "cpu")
+    m0 = {k: v.clone() for k, v in lr.model.state_dict().items()}
+    b1, b2 = synthetic_batch(conf, seed=1), synthetic_batch(conf, seed=2, first=False)
+    met1, tensors, _ = lr.step(b1)
+    assert {"loss_model", "loss_kl", "grad_norm", "grad_norm_actor", "grad_norm_critic", "grad_norm_probe"} <= set(met1)
+    assert 0 in lr.states and lr.states[0][0].shape == (conf.batch_size, conf.deter_dim)
+    met2, _, _ = lr.step(b2, do_image_pred=True)
+    assert "logprob_image" in met2 and lr.steps == 2
+    changed = sum(not torch.equal(m0[k], v) for k, v in lr.model.state_dict().items())
+    assert changed > 100                                      # parameters moved
+    path = str(tmp_path / "latest.pt")
+    lr.save_checkpoint(path)
+    ck = torch.load(path)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_0_state_dict", "optimizer_1_state_dict",
+                       "optimizer_2_state_dict", "optimizer_3_state_dict"}                       # tools.py:164-174
+    lr2 = Learner(conf, "cpu")
+    assert lr2.load_checkpoint(path) == 2
+    for (k, a), (_, b_) in zip(lr.model.state_dict().items(), lr2.model.state_dict().items()):
+        assert torch.equal(a, b_), k
+    # the reference module, if reachable, must load the checkpoint strictly (generator.py:109)
+    for cand in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "pydreamer")):
+            sys.path.insert(0, cand)
+            try:
+                from pydreamer.models import Dreamer as RefDreamer
+            except Exception:
+                continue
+            ref = RefDreamer(conf)
+            ref.load_state_dict(ck["model_state_dict"], strict=True)
+            out = ref.training_step(b1, ref.init_state(conf.batch_size))
+            assert torch.isfinite(out[0][0])
+            break
