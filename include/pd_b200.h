@@ -207,6 +207,14 @@ int pd_actor_loss_tanh_normal(pd_handle* h, long rows, int A, float eta, const f
 int pd_tanh_normal_sample(pd_handle* h, long rows, int A, const float* out, long ldo,
                           const float* eps, float* action, long lda, void* stream);
 
+/* ---- replay preprocessing on the device (pydreamer/preprocessing.py:91-188) ------------ */
+/* uint8 image (NB,H,W,C) -> fp32 (NB,C,H,W) = x/255 - 0.5 (preprocessing.py:21-29): the batch crosses PCIe as bytes. */
+int pd_image_u8_to_f32(pd_handle* h, long NB, int H, int W, int C, const uint8_t* src, float* dst, void* stream);
+/* int64 action index -> one-hot fp32 (preprocessing.py:135-138) */
+int pd_onehot_i64(pd_handle* h, long rows, int A, const int64_t* idx, float* out, void* stream);
+/* y = tanh(x): clip_rewards 'tanh' (functions.py:153-160) */
+int pd_tanh(pd_handle* h, long n, const float* x, float* y, void* stream);
+
 /* ---- optimizer (dreamer.py:60-87, train.py:193-198) ---------------------------------------- */
 int pd_sumsq(pd_handle* h, const float* x, long n, float* out /* += */, void* stream);
 /* norm = sqrt(*sumsq); coef = min(1, max_norm/(norm+1e-6)); x *= coef; *norm_out = norm

@@ -356,6 +356,17 @@ class RefOps:
         sd = F.softplus(out[:, A:2 * A]) + 0.1
         action.copy_(torch.tanh(mu + sd * eps.reshape(rows, A)))
 
+    # ------------------------------------------------------------------ preprocessing (preprocessing.py:21-29,135-138)
+    def image_u8_to_f32(self, src, dst):
+        x = src.to(torch.float32) / 255.0 - 0.5
+        dst.copy_(x.movedim(-1, -3))
+
+    def onehot_i64(self, idx, out):
+        out.copy_(F.one_hot(idx.long(), out.shape[-1]).to(out.dtype))
+
+    def tanh(self, x, y):
+        y.copy_(torch.tanh(x))
+
     # ------------------------------------------------------------------ optimizer
     def sumsq(self, x, out):
         out.add_((x * x).sum())

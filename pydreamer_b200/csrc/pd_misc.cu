@@ -485,3 +485,46 @@ int pd_inc(pd_handle* h, int32_t* counter, void* stream) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ replay preprocessing on the device
+namespace {
+// image uint8 (T*B, H, W, C) -> fp32 (T*B, C, H, W) = x / 255 - 0.5   (preprocessing.py:21-29 to_image)
+__global__ void image_u8_to_f32_kernel(long NB, int H, int W, int C, const uint8_t* __restrict__ src, float* __restrict__ dst) {
+    const long plane = (long)H * W;
+    GRID_STRIDE(i, NB * C * plane) {
+        long n = i / (C * plane);
+        long r = i - n * C * plane;
+        int c = (int)(r / plane);
+        long yx = r - (long)c * plane;
+        dst[i] = __fdiv_rn((float)src[(n * plane + yx) * C + c], 255.0f) - 0.5f;
+    }
+}
+// action index (int64) -> one-hot fp32 (preprocessing.py:135-138 to_onehot); reward -> tanh clip (functions.py:153-160)
+__global__ void onehot_i64_kernel(long rows, int A, const long long* __restrict__ idx, float* __restrict__ out) {
+    GRID_STRIDE(i, rows * A) {
+        long r = i / A; int c = (int)(i - r * A);
+        out[i] = (idx[r] == c) ? 1.f : 0.f;
+    }
+}
+__global__ void tanh_kernel(long n, const float* __restrict__ x, float* __restrict__ y) {
+    GRID_STRIDE(i, n) y[i] = tanhf(x[i]);
+}
+}  // namespace
+
+extern "C" {
+int pd_image_u8_to_f32(pd_handle* h, long NB, int H, int W, int C, const uint8_t* src, float* dst, void* stream) {
+    image_u8_to_f32_kernel<<<grid_for(NB * C * H * W, 256, h->num_sms), 256, 0, S(stream)>>>(NB, H, W, C, src, dst);
+    PD_CHECK_LAUNCH(h, "image_u8_to_f32");
+    return PD_OK;
+}
+int pd_onehot_i64(pd_handle* h, long rows, int A, const int64_t* idx, float* out, void* stream) {
+    onehot_i64_kernel<<<grid_for(rows * A, 256, h->num_sms), 256, 0, S(stream)>>>(rows, A, (const long long*)idx, out);
+    PD_CHECK_LAUNCH(h, "onehot_i64");
+    return PD_OK;
+}
+int pd_tanh(pd_handle* h, long n, const float* x, float* y, void* stream) {
+    tanh_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, S(stream)>>>(n, x, y);
+    PD_CHECK_LAUNCH(h, "tanh");
+    return PD_OK;
+}
+}

@@ -267,6 +267,18 @@ class NativeOps:
         self._ck(self.lib.pd_tanh_normal_sample(self.h, rows, A, _ptr(out), _ld(out), _ptr(eps), _ptr(action),
                                                 _ld(action), self._s()), "pd_tanh_normal_sample")
 
+    # ------------------------------------------------------------------ preprocessing
+    def image_u8_to_f32(self, src, dst):
+        NB = src.numel() // (src.shape[-1] * src.shape[-2] * src.shape[-3])
+        H, W, C = src.shape[-3:]
+        self._ck(self.lib.pd_image_u8_to_f32(self.h, NB, H, W, C, _ptr(src), _ptr(dst), self._s()), "pd_image_u8_to_f32")
+
+    def onehot_i64(self, idx, out):
+        self._ck(self.lib.pd_onehot_i64(self.h, idx.numel(), out.shape[-1], _ptr(idx), _ptr(out), self._s()), "pd_onehot_i64")
+
+    def tanh(self, x, y):
+        self._ck(self.lib.pd_tanh(self.h, x.numel(), _ptr(x), _ptr(y), self._s()), "pd_tanh")
+
     # ------------------------------------------------------------------ optimizer
     def sumsq(self, x, out):
         assert x.is_contiguous()
