@@ -74,6 +74,16 @@ int pd_gemm(pd_handle* h, int M, int N, int K,
 int pd_gemm_f16(pd_handle* h, int M, int N, int K, const void* A, long lda, const void* B, long ldb,
                 float* C, long ldc, const float* bias, const float* R, long ldr, int r_div,
                 int act, int round_out, void* stream);
+/* Implicit-GEMM convolution contractions: one operand is gathered on the fly from an NHWC fp32 tensor X[NB,H,W,C] by TMA
+ * im2col-mode loads (k x k taps, stride 2, no padding; P,Q = (H-k)/2+1) instead of a materialised im2col matrix.
+ *   mode 1: Cmat[NB*P*Q, odim] = im2col(X) * O        O: [odim][k*k*C] (o_mn=0) or [k*k*C][odim] (o_mn=1)
+ *           -> Conv2d forward (encoders.py:80-88) and ConvTranspose2d input gradient
+ *   mode 2: Cmat[k*k*cpad, odim] += im2col(X)^T * O   O: [NB*P*Q][odim]; rows (tap, channel) with channels padded to 32
+ *           -> ConvTranspose2d weight gradient
+ *   mode 3: Cmat[odim, k*k*cpad] += O^T * im2col(X)   O: [NB*P*Q][odim]
+ *           -> Conv2d weight gradient */
+int pd_conv_gemm(pd_handle* h, int mode, int NB, int H, int W, int C, int k, const float* X, const float* O, long ldo, int o_mn,
+                 int odim, float* Cmat, long ldc, const float* bias, int act, int round_out, int accumulate, void* stream);
 /* dst(fp16)[m, n] = src(fp32)[m, n] */
 int pd_to_half(pd_handle* h, long M, long N, const float* src, long lds, void* dst, long ldd, void* stream);
 
@@ -153,6 +163,7 @@ int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const flo
                     int act, float* db, void* stream);
 /* generic 4-D permutation copy out[perm(i)] (+)= in[i];  dims (HOST int[4]) of `in`, perm[j] (HOST) = source axis of out axis j. */
 int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, const int* perm,
+                const long* in_strides /* HOST long[4] element strides of `in`, or NULL = contiguous */,
                 int accumulate, int round_out, void* stream);
 
 /* ---- small pointwise / reductions ---------------------------------------------------------- */

@@ -68,6 +68,26 @@ class RefOps:
     def gemm_f16(self, A16, B16, C, *, bias=None, res=None, r_div=1, act=ACT_NONE, round_out=False):
         return self.gemm(A16.to(C.dtype), B16.to(C.dtype), C, bias=bias, res=res, r_div=r_div, act=act)
 
+    def conv_gemm(self, mode, X, k, O, Cmat, *, o_mn=False, bias=None, act=ACT_NONE, round_out=False):
+        NB, H, W, C = X.shape
+        P, Q = (H - k) // 2 + 1, (W - k) // 2 + 1
+        pat = X.unfold(1, k, 2).unfold(2, k, 2).permute(0, 1, 2, 4, 5, 3).reshape(NB * P * Q, k * k, C)   # (pixels, tap, c)
+        if mode == 1:
+            v = pat.reshape(NB * P * Q, k * k * C) @ (O if o_mn else O.t())
+            if bias is not None:
+                v = v + bias
+            Cmat.copy_(_act(v, act))
+            return Cmat
+        cpad = (C + 31) // 32 * 32
+        colp = torch.zeros(NB * P * Q, k * k, cpad, dtype=X.dtype, device=X.device)
+        colp[:, :, :C] = pat
+        colp = colp.reshape(NB * P * Q, k * k * cpad)
+        if mode == 2:
+            Cmat.add_(colp.t() @ O)
+        else:
+            Cmat.add_(O.t() @ colp)
+        return Cmat
+
     def to_half(self, src, dst):
         dst.copy_(src.to(dst.dtype))
 

@@ -7,6 +7,9 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
 int pd_gemm_simt_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
                         long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream);
 
+int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int k, const float* X, const float* O, long ldo,
+                        int o_mn, int ODIM, const PdEpilogue& epi, cudaStream_t stream);
+
 extern "C" {
 
 const char* pd_version(void) { return "pd_b200 0.1 (sm_100a; tcgen05 tf32 + TMA)"; }
@@ -74,6 +77,17 @@ int pd_gemm(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_m
     if (h->gemm_impl == PD_GEMM_SIMT || !tma_ok)
         return pd_gemm_simt_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream);
     return pd_gemm_tcgen05_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream, 0);
+}
+
+int pd_conv_gemm(pd_handle* h, int mode, int NB, int H, int W, int C, int k, const float* X, const float* O, long ldo, int o_mn,
+                 int odim, float* Cmat, long ldc, const float* bias, int act, int round_out, int accumulate, void* stream) {
+    if (!h) return PD_ERR_ARG;
+    PD_REQUIRE(h, mode >= 1 && mode <= 3 && X && O && Cmat, "pd_conv_gemm: bad arguments");
+    PD_REQUIRE(h, (mode == 1) == (accumulate == 0), "pd_conv_gemm: mode 1 stores, modes 2/3 accumulate");
+    PdEpilogue e;
+    e.C = Cmat; e.ldc = ldc; e.bias = bias; e.R = nullptr; e.ldr = 0; e.r_div = 1;
+    e.act = act; e.round_out = round_out; e.accumulate = accumulate; e.c_zeroed = 0;
+    return pd_conv_gemm_launch(h, mode, NB, H, W, C, k, X, O, ldo, o_mn, odim, e, (cudaStream_t)stream);
 }
 
 int pd_gemm_f16(pd_handle* h, int M, int N, int K, const void* A, long lda, const void* B, long ldb, float* C, long ldc,

@@ -20,6 +20,7 @@ struct pd_handle {
     long launches;            // kernels launched through this handle
     char err[512];
     void* encode_tiled;       // cuTensorMapEncodeTiled entry point
+    void* encode_im2col;      // cuTensorMapEncodeIm2col entry point (lazy)
     int gemm_smem_configured;
     int gemm_2cta;            // allow the cta_group::2 256x256 kernel for large problems
     int gemm2_smem_configured;

@@ -230,7 +230,7 @@ __global__ void bias_act_bwd_kernel(long M, int N, float* __restrict__ dy, long 
     }
 }
 
-struct Perm4 { int d[4]; long so[4]; };   // d: dims of `in`; so[a]: stride in `out` of in-axis a
+struct Perm4 { int d[4]; long so[4]; long si[4]; };   // d: dims of `in`; so[a] / si[a]: stride in `out` / `in` of in-axis a
 
 __global__ void permute4_kernel(long total, Perm4 p, const float* __restrict__ in, float* __restrict__ out,
                                 int accumulate, int round_out) {
@@ -241,7 +241,7 @@ __global__ void permute4_kernel(long total, Perm4 p, const float* __restrict__ i
         int i1 = (int)(t % p.d[1]); t /= p.d[1];
         int i0 = (int)t;
         long o = i0 * p.so[0] + i1 * p.so[1] + i2 * p.so[2] + i3 * p.so[3];
-        float v = in[idx];
+        float v = in[i0 * p.si[0] + i1 * p.si[1] + i2 * p.si[2] + i3 * p.si[3]];
         if (accumulate) out[o] += v;
         else out[o] = pd_round_if(v, round_out);
     }
@@ -330,8 +330,8 @@ int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const flo
     return PD_OK;
 }
 
-int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, const int* perm, int accumulate,
-                int round_out, void* stream) {
+int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, const int* perm, const long* in_strides,
+                int accumulate, int round_out, void* stream) {
     // out axis j takes in axis perm[j]; out is contiguous in its own (permuted) shape.
     Perm4 p;
     long ostride[4];
@@ -339,6 +339,10 @@ int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, cons
     for (int j = 3; j >= 0; --j) { ostride[j] = s; s *= dims[perm[j]]; }
     for (int a = 0; a < 4; ++a) p.d[a] = dims[a];
     for (int j = 0; j < 4; ++j) p.so[perm[j]] = ostride[j];
+    {
+        long st = 1;
+        for (int a = 3; a >= 0; --a) { p.si[a] = in_strides ? in_strides[a] : st; st *= dims[a]; }
+    }
     long total = (long)dims[0] * dims[1] * dims[2] * dims[3];
     permute4_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(total, p, in, out, accumulate,
                                                                                       round_out && h->round_ops);

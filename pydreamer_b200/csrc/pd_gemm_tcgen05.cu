@@ -39,6 +39,12 @@ struct GemmArgs {
     int a_mn, b_mn;
     int num_m, num_n, splits, kb_total, kb_per_split;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
+    // implicit-GEMM convolution operands (TMA im2col mode on an NHWC tensor, k x k taps, stride 2, no padding):
+    //   a_mode 1: A rows = output pixels, K = (tap, channel)            (conv forward / deconv input-gradient)
+    //   a_mode 2: A' rows = (tap, channel padded to 32), K = output pixels  (deconv weight gradient)
+    //   b_mode 2: B' rows = (tap, channel padded to 32), K = output pixels  (conv weight gradient)
+    int a_mode, b_mode;
+    int cv_PQ, cv_Q, cv_C, cv_k, cv_cblocks, cv_cpad;
     int f16;                   // operands are fp16 (kind::f16, 64 elements per 128-byte k-block) instead of tf32
     int tma_store;             // C is TMA-addressable: epilogue uses cp.async.bulk.tensor store / reduce
     int extras_on_split0;      // split-K of a plain (non-accumulate) GEMM: split 0 adds bias/residual, C pre-zeroed
@@ -78,6 +84,14 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(const void* tmap, uint64_t* bar, void* smem, int c, int w, int h, int n,
+                                                int off_w, int off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"((uint16_t)off_w), "h"((uint16_t)off_h)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -184,20 +198,52 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    const int k0 = kb * (g.f16 ? 2 * BK : BK);
-                    if (!g.a_mn) {
-                        tma_load_2d(&tmA, &full[stage], sa, k0, m0);              // box {32 k, 128 m}
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < BM / 32; ++j)                        // box {32 m, 32 k} x 4
-                            tma_load_2d(&tmA, &full[stage], sa + j * 4096, m0 + j * 32, k0);
+                    int k0 = kb * (g.f16 ? 2 * BK : BK);
+                    if (g.a_mode == 1) {
+                        // implicit im2col rows: k-block = 32 channels of one filter tap; pixel tile starts at m0
+                        const int tap = kb / g.cv_cblocks, c0 = (kb - tap * g.cv_cblocks) * 32;
+                        const int kh = tap / g.cv_k, kw = tap - kh * g.cv_k;
+                        const int n_ = m0 / g.cv_PQ, r_ = m0 - n_ * g.cv_PQ;
+                        const int p_ = r_ / g.cv_Q, q_ = r_ - p_ * g.cv_Q;
+                        tma_load_im2col(&tmA, &full[stage], sa, c0, 2 * q_, 2 * p_, n_, kw, kh);   // 128 pixels x 32 ch
+                        k0 = tap * g.cv_C + c0;                       // matching rows of the (tap, channel)-major weight
+                    } else if (g.a_mode == 2 || g.b_mode == 2) {
+                        ;                                             // handled below (pixel k-blocks)
                     }
-                    if (!g.b_mn) {
-                        tma_load_2d(&tmB, &full[stage], sb, k0, n0);
-                    } else {
+                    if (g.a_mode == 2 || g.b_mode == 2) {
+                        // K = output pixels: k-block = 32 consecutive pixels starting at kb*32
+                        const int pix = kb * 32;
+                        const int n_ = pix / g.cv_PQ, r_ = pix - n_ * g.cv_PQ;
+                        const int p_ = r_ / g.cv_Q, q_ = r_ - p_ * g.cv_Q;
+                        const void* tm = g.a_mode == 2 ? (const void*)&tmA : (const void*)&tmB;
+                        uint8_t* dst = g.a_mode == 2 ? sa : sb;
+                        const int base = g.a_mode == 2 ? m0 : n0;
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j)
-                            tma_load_2d(&tmB, &full[stage], sb + j * 4096, n0 + j * 32, k0);
+                        for (int j = 0; j < 4; ++j) {                 // 4 boxes of 32 (tap, channel) rows x 32 pixels
+                            const int idx = base + 32 * j;
+                            int tap = idx / g.cv_cpad, c0 = idx - tap * g.cv_cpad;
+                            if (tap >= g.cv_k * g.cv_k) { tap = 0; c0 = g.cv_cpad + 32; }        // past the last tap: all-OOB -> zeros
+                            const int kh = tap / g.cv_k, kw = tap - kh * g.cv_k;
+                            tma_load_im2col(tm, &full[stage], dst + j * 4096, c0, 2 * q_, 2 * p_, n_, kw, kh);
+                        }
+                    }
+                    if (g.a_mode == 0) {
+                        if (!g.a_mn) {
+                            tma_load_2d(&tmA, &full[stage], sa, k0, m0);              // box {32 k, 128 m}
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / 32; ++j)                        // box {32 m, 32 k} x 4
+                                tma_load_2d(&tmA, &full[stage], sa + j * 4096, m0 + j * 32, k0);
+                        }
+                    }
+                    if (g.b_mode == 0) {
+                        if (!g.b_mn) {
+                            tma_load_2d(&tmB, &full[stage], sb, k0, n0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 32; ++j)
+                                tma_load_2d(&tmB, &full[stage], sb + j * 4096, n0 + j * 32, k0);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -659,7 +705,98 @@ int make_map(pd_handle* h, CUtensorMap* tm, const void* base, uint64_t dim0, uin
     return PD_OK;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA im2col-mode map over an NHWC fp32 tensor (k x k taps, stride 2, no padding): lower corner 0, upper corner -(k-1).
+int make_im2col_map(pd_handle* h, CUtensorMap* tm, const float* base, int NB, int H, int W, int C, int k, int pixels,
+                    CUtensorMapSwizzle swz) {
+    if (!h->encode_im2col) {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+            PD_FAIL(h, PD_ERR_DEVICE, "cuTensorMapEncodeIm2col entry point not found");
+        h->encode_im2col = p;
+    }
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    int lo[2] = {0, 0}, up[2] = {-(k - 1), -(k - 1)};
+    cuuint32_t estr[4] = {1, 2, 2, 1};
+    CUresult r = ((EncodeIm2colFn)h->encode_im2col)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, gdim, gstr, lo, up, 32,
+                                                   (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "cuTensorMapEncodeIm2col failed (%d): %dx%dx%dx%d k=%d", (int)r, NB, H, W, C, k);
+    return PD_OK;
+}
+
 }  // namespace
+
+// Implicit-GEMM convolution launcher.  mode 1: C[pixels, N] = im2col(X) * B   (B: [N][K] or, b_mn, [K][N]; K = (tap, c))
+//                                      mode 2: C[(tap,cpad), N] += im2col(X)^T * Bt   (Bt stored [pixels][N])
+//                                      mode 3: C[M, (tap,cpad)] += At^T * im2col(X)   (At stored [pixels][M])
+int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int k, const float* X, const float* O, long ldo,
+                        int o_mn, int ODIM, const PdEpilogue& epi, cudaStream_t stream) {
+    PD_REQUIRE(h, (C % 4) == 0 && ((((uintptr_t)X) & 15) == 0), "pd_conv_gemm: C %% 4 and 16-byte alignment required");
+    PD_REQUIRE(h, (ldo % 4) == 0 && ((((uintptr_t)O) & 15) == 0), "pd_conv_gemm: operand alignment");
+    PD_REQUIRE(h, (epi.ldc % 4) == 0 && ((((uintptr_t)epi.C) & 15) == 0), "pd_conv_gemm: C must be TMA-addressable");
+    if (!h->gemm_smem_configured) {
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
+        h->gemm_smem_configured = 1;
+    }
+    const int P = (H - k) / 2 + 1, Q = (W - k) / 2 + 1;
+    const long pixels = (long)NB * P * Q;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.cv_PQ = P * Q; g.cv_Q = Q; g.cv_C = C; g.cv_k = k; g.cv_cblocks = pd_cdiv(C, 32); g.cv_cpad = g.cv_cblocks * 32;
+    g.mn_lbo = 4096; g.mn_sbo = 512;
+    g.epi = epi; g.tma_store = 1;
+    CUtensorMap tmA, tmB, tmC;
+    int rc, M, N;
+    if (mode == 1) {
+        M = (int)pixels; N = ODIM;
+        g.a_mode = 1; g.a_mn = 0; g.b_mode = 0; g.b_mn = o_mn;
+        g.kb_total = k * k * g.cv_cblocks;
+        rc = make_im2col_map(h, &tmA, X, NB, H, W, C, k, BM, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
+        const long Ktot = (long)k * k * C;
+        if (!o_mn) rc = make_map(h, &tmB, O, (uint64_t)Ktot, (uint64_t)N, (uint64_t)ldo, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+        else       rc = make_map(h, &tmB, O, (uint64_t)N, (uint64_t)Ktot, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    } else if (mode == 2) {
+        M = k * k * g.cv_cpad; N = ODIM;
+        g.a_mode = 2; g.a_mn = 1; g.b_mode = 0; g.b_mn = 1;
+        g.kb_total = pd_cdiv(pixels, 32);
+        rc = make_im2col_map(h, &tmA, X, NB, H, W, C, k, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
+        rc = make_map(h, &tmB, O, (uint64_t)N, (uint64_t)pixels, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    } else {
+        M = ODIM; N = k * k * g.cv_cpad;
+        g.a_mode = 0; g.a_mn = 1; g.b_mode = 2; g.b_mn = 1;
+        g.kb_total = pd_cdiv(pixels, 32);
+        rc = make_map(h, &tmA, O, (uint64_t)M, (uint64_t)pixels, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+        rc = make_im2col_map(h, &tmB, X, NB, H, W, C, k, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
+    }
+    rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    g.M = M; g.N = N; g.K = 0;
+    g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
+    int tiles = g.num_m * g.num_n, splits = 1;
+    if (epi.accumulate && tiles < h->num_sms) {
+        splits = h->num_sms / tiles;
+        int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    g.kb_per_split = pd_cdiv(g.kb_total, splits);
+    g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
+    int units = tiles * g.splits;
+    int grid = units < h->num_sms ? units : h->num_sms;
+    pd_gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
+    PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel(im2col)");
+    return PD_OK;
+}
 
 int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, long lda, int a_mn, const void* B,
                            long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream, int f16) {
@@ -684,6 +821,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     if (rc) return rc;
 
     GemmArgs g;
+    memset(&g, 0, sizeof(g));
     g.M = M; g.N = N; g.K = K; g.a_mn = a_mn; g.b_mn = b_mn;
     g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
     g.f16 = f16;

@@ -376,6 +376,9 @@ class Dreamer(nn.Module):
     # forward-only layers (imagination rollout, heads on dreamed features) use fp16 tensor-core operands: the same
     # 10-bit mantissa as TF32 at twice the MMA rate and half the operand traffic; no gradient flows through them.
     fp16_forward = os.environ.get("PD_B200_FP16_FORWARD", "1") != "0"
+    # conv / deconv contractions gather their operand with TMA im2col-mode loads (pd_conv_gemm) instead of materialising
+    # im2col matrices: encoder layers 2-4 (forward + weight gradient), deconv layers 2-3 (input + weight gradient).
+    implicit_conv = os.environ.get("PD_B200_IMPLICIT_CONV", "1") != "0"
 
     # ------------------------------------------------------------------ reference API
     def init_optimizers(self, lr, lr_actor=None, lr_critic=None, eps=1e-5):
@@ -711,10 +714,13 @@ class Dreamer(nn.Module):
         geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
         x4 = img.permute(0, 2, 3, 1)
         for li, (hin, hout, ci, co) in enumerate(geo):
-            col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
-            ops.im2col(x4, 4, 1 if li == 0 else 0, col, round_out=True)
             act = b(f"enc.a{li}", NB * hout * hout, co)
-            ops.gemm(col, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
+            if li > 0 and self.implicit_conv:
+                ops.conv_gemm(1, x4, 4, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
+            else:
+                col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
+                ops.im2col(x4, 4, 1 if li == 0 else 0, col, round_out=True)
+                ops.gemm(col, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
             x4 = act.view(NB, hout, hout, co)
         embed = b("enc.embed", NB, d.E)
         ops.permute4(b("enc.a3", NB * 4, 8 * cd).view(NB, 4, 8 * cd, 1), embed.view(NB, 8 * cd, 4, 1), (0, 2, 1, 3),
@@ -903,21 +909,28 @@ class Dreamer(nn.Module):
         ops.rowscale(csum, w, 1, conf.image_weight)
         ops.colsum(csum, G(dec[8].bias))
         dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
-        gdec = [b(f"bwd.gdecw{li}", *self._decw[li].shape) for li in range(4)]
+        impl = [self.implicit_conv and li in (1, 2) for li in range(4)]   # deconv 2,3: 32-channel-aligned NHWC gradients
+        copad = [(dgeo[li][4] + 31) // 32 * 32 for li in range(4)]
+        gdec = [b(f"bwd.gdecwp{li}", dgeo[li][2] ** 2 * copad[li], dgeo[li][3]) if impl[li]
+                else b(f"bwd.gdecw{li}", *self._decw[li].shape) for li in range(4)]
         for g_ in gdec:
             ops.fill(g_, 0.0)
         dout4 = diff.permute(0, 2, 3, 1)                       # [n,y,x,c] view of the NCHW diff
         for li in (3, 2, 1, 0):
             hi, ho, k, ci, co = dgeo[li]
             xin = b("dec.x0", N, 32 * cd) if li == 0 else b(f"dec.d{li - 1}", N, hi, hi, ci).view(N * hi * hi, ci)
-            if li == 0:
-                dcols = dout4.reshape(N, k * k * co)           # 5x5 input of a 5x5 kernel: im2col is the identity
-            else:
-                dcols = b(f"bwd.dcols{li}", N * hi * hi, k * k * co)
-                ops.im2col(dout4, k, 0, dcols, round_out=True)
-            ops.gemm(dcols, xin, gdec[li], a_mn=True, b_mn=True, accumulate=True)
             dxin = b(f"bwd.dd{li}", N * hi * hi, ci)
-            ops.gemm(dcols, self._decw[li], dxin, b_mn=True, round_out=(li == 0))
+            if impl[li]:
+                ops.conv_gemm(2, dout4, k, xin, gdec[li])                              # weight gradient, rows (tap, co padded)
+                ops.conv_gemm(1, dout4, k, self._decw[li], dxin, o_mn=True)            # input gradient
+            else:
+                if li == 0:
+                    dcols = dout4.reshape(N, k * k * co)       # 5x5 input of a 5x5 kernel: im2col is the identity
+                else:
+                    dcols = b(f"bwd.dcols{li}", N * hi * hi, k * k * co)
+                    ops.im2col(dout4, k, 0, dcols, round_out=True)
+                ops.gemm(dcols, xin, gdec[li], a_mn=True, b_mn=True, accumulate=True)
+                ops.gemm(dcols, self._decw[li], dxin, b_mn=True, round_out=(li == 0))
             if li > 0:
                 ops.bias_act_bwd(dxin, xin, ACT_ELU, G(dec[2 * li].bias))       # bias of the previous deconv
                 dout4 = dxin.view(N, hi, hi, ci)
@@ -926,7 +939,8 @@ class Dreamer(nn.Module):
         for li, idx_ in enumerate((2, 4, 6, 8)):              # back to ConvTranspose2d layout (Cin,Cout,kh,kw)
             wt = dec[idx_].weight
             ci, co, kh, kw = wt.shape
-            ops.permute4(gdec[li].view(kh, kw, co, ci), G(wt), (3, 2, 0, 1))
+            src = gdec[li].view(kh, kw, copad[li], ci)[:, :, :co] if impl[li] else gdec[li].view(kh, kw, co, ci)
+            ops.permute4(src, G(wt), (3, 2, 0, 1))
         ops.gemm(dx0, featN, G(dec[0].weight), a_mn=True, b_mn=True, accumulate=True)
         ops.colsum(dx0, G(dec[0].bias))
         ops.gemm(dx0, W(dec[0].weight), dfeat, b_mn=True)                      # first writer of dfeat
@@ -1015,15 +1029,24 @@ class Dreamer(nn.Module):
         for li in (3, 2, 1, 0):
             hin_, hout, ci, co = geo[li]
             act = b(f"enc.a{li}", NB * hout * hout, co)
-            col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
             ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
             if li == 0:
+                col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
                 ops.gemm(da, col, G(enc[0].weight).view(co, 16 * ci), a_mn=True, b_mn=True, accumulate=True)
             else:
-                gw = b(f"bwd.gencw{li}", co, 16 * ci)
-                ops.fill(gw, 0.0)
-                ops.gemm(da, col, gw, a_mn=True, b_mn=True, accumulate=True)
-                ops.permute4(gw.view(co, 4, 4, ci), G(enc[2 * li].weight), (0, 3, 1, 2))
+                if self.implicit_conv:
+                    cpad = (ci + 31) // 32 * 32                   # (tap, channel) columns with channels padded to 32
+                    gw = b(f"bwd.gencwp{li}", co, 16 * cpad)
+                    ops.fill(gw, 0.0)
+                    xprev = b(f"enc.a{li - 1}", NB * hin_ * hin_, ci).view(NB, hin_, hin_, ci)
+                    ops.conv_gemm(3, xprev, 4, da, gw)
+                    ops.permute4(gw.view(co, 4, 4, cpad)[..., :ci], G(enc[2 * li].weight), (0, 3, 1, 2))
+                else:
+                    col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
+                    gw = b(f"bwd.gencw{li}", co, 16 * ci)
+                    ops.fill(gw, 0.0)
+                    ops.gemm(da, col, gw, a_mn=True, b_mn=True, accumulate=True)
+                    ops.permute4(gw.view(co, 4, 4, ci), G(enc[2 * li].weight), (0, 3, 1, 2))
                 dcol = b(f"bwd.dcol{li}", NB * hout * hout, 16 * ci)
                 ops.gemm(da, self._encw[li], dcol, b_mn=True)
                 da_prev = b(f"bwd.da{li - 1}", NB * hin_ * hin_, ci)

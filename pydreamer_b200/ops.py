@@ -110,6 +110,16 @@ class NativeOps:
             prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, "f16", 0, 0)))
         return C
 
+    def conv_gemm(self, mode, X, k, O, Cmat, *, o_mn=False, bias=None, act=ACT_NONE, round_out=False):
+        """Implicit-GEMM convolution contraction (pd_conv_gemm): X is a contiguous NHWC tensor (NB,H,W,C)."""
+        NB, H, W, C = X.shape
+        assert X.is_contiguous()
+        odim = Cmat.shape[1] if mode in (1, 2) else Cmat.shape[0]
+        self._ck(self.lib.pd_conv_gemm(self.h, int(mode), NB, H, W, C, int(k), _ptr(X), _ptr(O), _ld(O), int(o_mn), odim,
+                                       _ptr(Cmat), _ld(Cmat), _ptr(bias), int(act), int(round_out), 0 if mode == 1 else 1,
+                                       self._s()), "pd_conv_gemm")
+        return Cmat
+
     def to_half(self, src, dst):
         M, N = src.shape
         self._ck(self.lib.pd_to_half(self.h, M, N, _ptr(src), _ld(src), _ptr(dst), _ld(dst), self._s()), "pd_to_half")
@@ -189,10 +199,11 @@ class NativeOps:
 
     def permute4(self, inp, out, perm, accumulate=False, round_out=False):
         """out (contiguous, shape = inp.shape permuted by perm) (+)= inp.permute(perm)."""
-        assert inp.is_contiguous() and out.is_contiguous() and inp.dim() == 4
+        assert out.is_contiguous() and inp.dim() == 4
         dims = (ctypes.c_int * 4)(*inp.shape)
         pm = (ctypes.c_int * 4)(*perm)
-        self._ck(self.lib.pd_permute4(self.h, _ptr(inp), _ptr(out), dims, pm, int(accumulate), int(round_out),
+        st = None if inp.is_contiguous() else (ctypes.c_long * 4)(*inp.stride())
+        self._ck(self.lib.pd_permute4(self.h, _ptr(inp), _ptr(out), dims, pm, st, int(accumulate), int(round_out),
                                       self._s()), "pd_permute4")
 
     # ------------------------------------------------------------------ small ops

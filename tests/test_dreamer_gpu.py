@@ -23,6 +23,7 @@ def run_gpu(case, impl, rounding):
     model = Dreamer(conf).to(DEV)
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     model.fp16_forward = (impl == 0)          # the exact arm keeps every GEMM in fp32
+    model.implicit_conv = (impl == 0)         # ... and uses the explicit im2col + SIMT GEMM path
     model._ensure_arena()
     model.ops.set_gemm_impl(impl)
     model.ops.set_round_operands(rounding)

@@ -458,3 +458,30 @@ def test_fp16_side_outputs_of_producers(ops, ref):
     src, dst = rnd(77, 130), torch.empty(77, 130, device=DEV, dtype=torch.float16)
     ops.to_half(src, dst)
     assert torch.equal(dst, src.half())
+
+
+@pytest.mark.parametrize("NB,H,C,k,odim", [(3, 14, 96, 4, 192), (2, 31, 48, 4, 96), (3, 13, 96, 5, 192), (2, 30, 48, 6, 96),
+                                             (5, 6, 192, 4, 384), (7, 5, 192, 5, 1536)])
+def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
+    """TMA im2col-mode operands (no materialised im2col matrix): conv forward / deconv dX (mode 1, both weight layouts),
+    deconv weight gradient (mode 2) and conv weight gradient (mode 3).  Integer operands: bit-exact."""
+    if DEV == "cpu":
+        pytest.skip("dry run")
+    ops.set_gemm_impl(0)
+    P = (H - k) // 2 + 1
+    pixels, K = NB * P * P, k * k * C
+    cpad = (C + 31) // 32 * 32
+    X = ints(NB, H, H, C, seed=1, lo=-2, hi=3)
+    Wk, bias = ints(odim, K, seed=2, lo=-2, hi=3), ints(odim, seed=3)
+    for o_mn, O in ((False, Wk), (True, Wk.t().contiguous())):
+        C1, C1r = torch.full((pixels, odim), float("nan"), device=DEV), torch.empty(pixels, odim, device=DEV)
+        ops.conv_gemm(1, X, k, O, C1, o_mn=o_mn, bias=bias, act=1)
+        ref.conv_gemm(1, X, k, O, C1r, o_mn=o_mn, bias=bias, act=1)
+        close(C1, C1r, 1e-6, 1e-6, f"conv_gemm mode 1 o_mn={o_mn}")
+    Ot = ints(pixels, odim, seed=4, lo=-2, hi=3)
+    C2, C3 = ints(k * k * cpad, odim, seed=5), ints(odim, k * k * cpad, seed=6)
+    C2r, C3r = C2.clone(), C3.clone()
+    ops.conv_gemm(2, X, k, Ot, C2); ref.conv_gemm(2, X, k, Ot, C2r)
+    assert torch.equal(C2, C2r), f"mode 2 max diff {(C2 - C2r).abs().max().item()}"
+    ops.conv_gemm(3, X, k, Ot, C3); ref.conv_gemm(3, X, k, Ot, C3r)
+    assert torch.equal(C3, C3r), f"mode 3 max diff {(C3 - C3r).abs().max().item()}"
