@@ -115,9 +115,17 @@ class NativeOps:
         NB, H, W, C = X.shape
         assert X.is_contiguous()
         odim = Cmat.shape[1] if mode in (1, 2) else Cmat.shape[0]
+        prof = self.gemm_profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self._ck(self.lib.pd_conv_gemm(self.h, int(mode), NB, H, W, C, int(k), _ptr(X), _ptr(O), _ld(O), int(o_mn), odim,
                                        _ptr(Cmat), _ld(Cmat), _ptr(bias), int(act), int(round_out), 0 if mode == 1 else 1,
                                        self._s()), "pd_conv_gemm")
+        if prof is not None:
+            e1.record()
+            P, Q = (H - k) // 2 + 1, (W - k) // 2 + 1
+            prof.append((e0, e1, 2.0 * NB * P * Q * k * k * C * odim, (NB * P * Q, odim, k * k * C, f"conv{mode}", int(o_mn), 0)))
         return Cmat
 
     def to_half(self, src, dst):
