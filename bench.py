@@ -46,7 +46,13 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=0, help="sequences per reference sample step (0 = auto)")
     ap.add_argument("--dump-gemm-profile", default="", help="write the per-shape GEMM timing table of one step here")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU reference (0 = calibrate)")
-    return ap.parse_args()
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("PD_BENCH_WATCHDOG", "0")),
+                    help="dump all Python stacks to stderr and exit after this many seconds (0 = off)")
+    a = ap.parse_args()
+    if a.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(a.watchdog, exit=True)
+    return a
 
 
 def peaks():

@@ -16,6 +16,7 @@ so `loss.backward()` in the caller works unchanged.  Parameters live in one flat
 is what the fused optimizer and the single-bucket data-parallel all-reduce operate on.
 """
 import math
+import contextlib
 import os
 from types import SimpleNamespace
 
@@ -520,13 +521,13 @@ class Dreamer(nn.Module):
                 mean = self._buf(f"{tag}.m{l}", RT)[row0:row0 + rows]
                 rstd = self._buf(f"{tag}.r{l}", RT)[row0:row0 + rows]
             else:
-                x = self._buf(f"mlp.sx", rows, mp.hid)
-                y = self._buf(f"mlp.sy{l % 2}", rows, mp.hid)
-                mean = self._buf("mlp.sm", rows)
-                rstd = self._buf("mlp.sr", rows)
+                x = self._buf(f"{self._scratch_ns}mlp.sx", rows, mp.hid)
+                y = self._buf(f"{self._scratch_ns}mlp.sy{l % 2}", rows, mp.hid)
+                mean = self._buf(f"{self._scratch_ns}mlp.sm", rows)
+                rstd = self._buf(f"{self._scratch_ns}mlp.sr", rows)
             if f16:
                 ops.gemm_f16(inp16, self._wh(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
-                y16 = self._buf(f"mlp.h16_{l % 2}", rows, mp.hid, dtype=torch.float16)
+                y16 = self._buf(f"{self._scratch_ns}mlp.h16_{l % 2}", rows, mp.hid, dtype=torch.float16)
             else:
                 ops.gemm(inp, self._w(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
                 y16 = None
@@ -542,8 +543,8 @@ class Dreamer(nn.Module):
         RT = rows_total or rows
         sv = lambda n, l: self._buf(f"{tag}.{n}{l}", RT, mp.hid)[:rows]
         st = lambda n, l: self._buf(f"{tag}.{n}{l}", RT)[:rows]
-        dy = self._buf("mlp.dy", rows, mp.hid)
-        dx = self._buf("mlp.dx", rows, mp.hid)
+        dy = self._buf(f"{self._scratch_ns}mlp.dy", rows, mp.hid)
+        dx = self._buf(f"{self._scratch_ns}mlp.dx", rows, mp.hid)
         ylast = sv("y", mp.L - 1)
         ops.gemm(dout, ylast, self._g(mp.out.weight), a_mn=True, b_mn=True, accumulate=True)
         ops.colsum(dout, self._g(mp.out.bias))
@@ -630,21 +631,43 @@ class Dreamer(nn.Module):
         tm = self._phase_timer
         if tm is not None:
             tm.mark("prepare+noise")
+        par = self._ov(1)
+        ac_box = {}
+
+        def run_ac():
+            feats = self._buf("feats", H + 1, N, self.d.F)
+            self._dream(feats, N, H, noise["actor"], noise["prior"], "")
+            if tm is not None:
+                tm.mark("dream")
+            ac_box["out"] = self._actor_critic(feats, N, H, want_grad, "")
+            if tm is not None:
+                tm.mark("actor_critic")
+
+        def after_features():                       # the dream needs only the (detached) posterior features
+            if par:
+                self._scratch_ns = "ac."
+                try:
+                    with self._fork(1):
+                        run_ac()
+                finally:
+                    self._scratch_ns = ""
+
         wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"], open_loop,
-                                  noise["image_pred"] if image_pred else None)
+                                  noise["image_pred"] if image_pred else None, after_features=after_features)
         if tm is not None:
             tm.mark("wm_forward")
         if want_grad:
             self._wm_backward(obs, T, B, I, H)
         if tm is not None:
             tm.mark("wm_backward")
-        feats = self._buf("feats", H + 1, N, self.d.F)
-        self._dream(feats, N, H, noise["actor"], noise["prior"], "")
-        if tm is not None:
-            tm.mark("dream")
-        ac_out = self._actor_critic(feats, N, H, want_grad, "")
-        if tm is not None:
-            tm.mark("actor_critic")
+        if par:
+            self._join(1)
+            cur = torch.cuda.current_stream(self._arena.device)
+            for v in ac_box["out"]["metrics"].values():       # allocated on the side stream, consumed on this one
+                v.record_stream(cur)
+        else:
+            run_ac()
+        ac_out = ac_box["out"]
         if dream_log:
             ac_out["dream_tensors"] = self._dream_for_log(obs, T, B, I, noise["dream_log_actor"], noise["dream_log_prior"])
         return wm_out, ac_out
@@ -661,6 +684,35 @@ class Dreamer(nn.Module):
 
     # set PD_B200_GRAPHS=0 to launch every kernel from Python instead of replaying a captured CUDA graph
     use_cuda_graph = os.environ.get("PD_B200_GRAPHS", "1") != "0"
+
+    # Independent parts of the step are issued on side streams (parallel branches of the captured graph), so the
+    # latency-bound M=B recurrent chains share the GPU with throughput-bound work instead of idling it.  Bit mask:
+    #   1  dream + actor-critic (needs only the detached features) alongside decoder / losses / world-model backward
+    #   2  the h·W_hh GEMM of the next step (and its transpose in BPTT) off the per-timestep critical path
+    #   4  image-decoder weight gradients alongside the input-gradient chain and BPTT
+    # (Measured, profiles/README.md: 1 is worth 4.5 ms of 36; 2 and 4 are within noise; running the encoder in time
+    #  chunks beside the unroll / BPTT gained nothing - the split-K chain GEMMs already occupy every SM.)
+    overlap = int(os.environ.get("PD_B200_OVERLAP", "3"))
+    _scratch_ns = ""          # name space of the shared MLP scratch buffers (one per concurrent branch)
+
+    def _ov(self, bit):
+        return bool(self.overlap & bit) and self._arena.is_cuda and self._phase_timer is None
+
+    def _side(self, k):
+        key = (k, torch.cuda.current_stream(self._arena.device).cuda_stream)     # one side stream per (purpose, parent)
+        st = self.__dict__.setdefault("_side_streams", {})
+        if key not in st:
+            st[key] = torch.cuda.Stream(device=self._arena.device)
+        return st[key]
+
+    def _fork(self, k):
+        """Context manager: the block is issued on side stream k, ordered after everything issued so far."""
+        s = self._side(k)
+        s.wait_stream(torch.cuda.current_stream(self._arena.device))
+        return torch.cuda.stream(s)
+
+    def _join(self, k):
+        torch.cuda.current_stream(self._arena.device).wait_stream(self._side(k))
 
     def _graphed_core(self, obs, in_state, T, B, I, H):
         """CUDA-graph replay of `_core` (the ~1 400 kernel launches of a step are issued by one cudaGraphLaunch).
@@ -712,25 +764,32 @@ class Dreamer(nn.Module):
         # ---- encoder (encoders.py:72-96): im2col -> tcgen05 GEMM (+bias+ELU) x4, NHWC activations
         img = obs["image"].reshape(NB, IC, 64, 64)
         geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
-        x4 = img.permute(0, 2, 3, 1)
-        for li, (hin, hout, ci, co) in enumerate(geo):
-            act = b(f"enc.a{li}", NB * hout * hout, co)
-            if li > 0 and self.implicit_conv:
-                ops.conv_gemm(1, x4, 4, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
-            else:
-                col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
-                ops.im2col(x4, 4, 1 if li == 0 else 0, col, round_out=True)
-                ops.gemm(col, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
-            x4 = act.view(NB, hout, hout, co)
         embed = b("enc.embed", NB, d.E)
-        ops.permute4(b("enc.a3", NB * 4, 8 * cd).view(NB, 4, 8 * cd, 1), embed.view(NB, 8 * cd, 4, 1), (0, 2, 1, 3),
-                     round_out=True)                                           # (h,w,c) -> reference (c,h,w) flatten
+        ea = b("rssm.ea", NB, d.Hd)
+
+        def encode(r0, r1):                         # images [r0, r1) -> embed rows -> hoisted post_mlp_e product
+            x4 = img[r0:r1].permute(0, 2, 3, 1)
+            for li, (hin_, hout, ci, co) in enumerate(geo):
+                hw = hout * hout
+                act = b(f"enc.a{li}", NB * hw, co)[r0 * hw:r1 * hw]
+                if li > 0 and self.implicit_conv:
+                    ops.conv_gemm(1, x4, 4, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU,
+                                  round_out=True)
+                else:
+                    col = b(f"enc.col{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
+                    ops.im2col(x4, 4, 1 if li == 0 else 0, col, round_out=True)
+                    ops.gemm(col, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU, round_out=True)
+                x4 = act.view(r1 - r0, hout, hout, co)
+            ops.permute4(x4.view(r1 - r0, 4, 8 * cd, 1), embed[r0:r1].view(r1 - r0, 8 * cd, 4, 1), (0, 2, 1, 3),
+                         round_out=True)                                       # (h,w,c) -> reference (c,h,w) flatten
+            ops.gemm(embed[r0:r1], self._w(cell.post_mlp_e.weight), ea[r0:r1])  # hoisted over T
+
+        encode(0, NB)
 
         # ---- RSSM posterior unroll (rssm.py:21-78, 125-153)
         mask = b("rssm.mask", T, BI)
         ops.reset_mask(obs["reset"], I, mask)
         action = obs["action"].reshape(NB, d.A)
-        ea = b("rssm.ea", NB, d.Hd); ops.gemm(embed, self._w(cell.post_mlp_e.weight), ea)      # hoisted over T
         aa = b("rssm.aa", NB, d.Hd); ops.gemm(action, self._w(cell.a_mlp.weight), aa)
         hin, zin = b("rssm.hin", T, BI, d.D), b("rssm.zin", T, BI, d.Z)
         ops.mask_rows(in_state[0], mask[0], hin[0]); ops.mask_rows(in_state[1], mask[0], zin[0])
@@ -747,15 +806,26 @@ class Dreamer(nn.Module):
         if skinny:
             for buf_ in (x1, gi, gh, y2, post):
                 ops.fill(buf_, 0.0)
+        par = self._ov(2)
+        gh_gemm = lambda t: ops.gemm(hin[t], W(gru.weight_hh), gh[t], bias=self._raw(gru.bias_hh), c_zeroed=skinny)
+        if par:
+            with self._fork(2):
+                gh_gemm(0)
         for t in range(T):
             last = t == T - 1
             ops.gemm(zin[t], W(cell.z_mlp.weight), x1[t], bias=self._raw(cell.z_mlp.bias), res=aa[t * B:(t + 1) * B],
                      r_div=I, c_zeroed=skinny)
             ops.ln_elu_fwd(x1[t], self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za[t], m1[t], r1[t])
             ops.gemm(za[t], W(gru.weight_ih), gi[t], bias=self._raw(gru.bias_ih), c_zeroed=skinny)
-            ops.gemm(hin[t], W(gru.weight_hh), gh[t], bias=self._raw(gru.bias_hh), c_zeroed=skinny)
+            if par:
+                self._join(2)
+            else:
+                gh_gemm(t)
             ops.gru_fwd(gi[t], gh[t], hin[t], feat[t, :, :d.D], None if last else hin[t + 1],
                         None if last else mask[t + 1], gates[t])
+            if par and not last:                    # h_{t+1} is known: its W_hh product overlaps the posterior MLP
+                with self._fork(2):
+                    gh_gemm(t + 1)
             if not open_loop:
                 ops.gemm(feat[t, :, :d.D], W(cell.post_mlp_h.weight), y2[t], bias=self._raw(cell.post_mlp_h.bias),
                          res=ea[t * B:(t + 1) * B], r_div=I, c_zeroed=skinny)
@@ -773,7 +843,8 @@ class Dreamer(nn.Module):
         out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
         return img, post, idx, out_state
 
-    def _wm_forward(self, obs, in_state, T, B, I, H, noise_post, open_loop=False, noise_image_pred=None):
+    def _wm_forward(self, obs, in_state, T, B, I, H, noise_post, open_loop=False, noise_image_pred=None,
+                    after_features=None):
         ops, d, conf = self.ops, self.d, self.conf
         NB, BI = T * B, B * I
         N = NB * I
@@ -782,6 +853,8 @@ class Dreamer(nn.Module):
         feats = b("feats", H + 1, N, d.F)            # feats[0] = world-model features, feats[1:] = dream
         img, post, idx, out_state = self._wm_features(obs, in_state, T, B, I, noise_post, "", feats[0].view(T, BI, d.F),
                                                       open_loop)
+        if after_features is not None:
+            after_features()
         featN = feats[0]                                   # (N, F)
         hN = featN[:, :d.D]
         # batched prior (rssm.py:186-193)
@@ -915,13 +988,16 @@ class Dreamer(nn.Module):
                 else b(f"bwd.gdecw{li}", *self._decw[li].shape) for li in range(4)]
         for g_ in gdec:
             ops.fill(g_, 0.0)
+        par_w = self._ov(4)                 # weight gradients leave the dfeat -> BPTT critical path (joined at the end)
+        side = (lambda: self._fork(4)) if par_w else contextlib.nullcontext
         dout4 = diff.permute(0, 2, 3, 1)                       # [n,y,x,c] view of the NCHW diff
         for li in (3, 2, 1, 0):
             hi, ho, k, ci, co = dgeo[li]
             xin = b("dec.x0", N, 32 * cd) if li == 0 else b(f"dec.d{li - 1}", N, hi, hi, ci).view(N * hi * hi, ci)
             dxin = b(f"bwd.dd{li}", N * hi * hi, ci)
             if impl[li]:
-                ops.conv_gemm(2, dout4, k, xin, gdec[li])                              # weight gradient, rows (tap, co padded)
+                with side():
+                    ops.conv_gemm(2, dout4, k, xin, gdec[li])                          # weight gradient, rows (tap, co padded)
                 ops.conv_gemm(1, dout4, k, self._decw[li], dxin, o_mn=True)            # input gradient
             else:
                 if li == 0:
@@ -929,20 +1005,22 @@ class Dreamer(nn.Module):
                 else:
                     dcols = b(f"bwd.dcols{li}", N * hi * hi, k * k * co)
                     ops.im2col(dout4, k, 0, dcols, round_out=True)
-                ops.gemm(dcols, xin, gdec[li], a_mn=True, b_mn=True, accumulate=True)
+                with side():
+                    ops.gemm(dcols, xin, gdec[li], a_mn=True, b_mn=True, accumulate=True)
                 ops.gemm(dcols, self._decw[li], dxin, b_mn=True, round_out=(li == 0))
             if li > 0:
                 ops.bias_act_bwd(dxin, xin, ACT_ELU, G(dec[2 * li].bias))       # bias of the previous deconv
                 dout4 = dxin.view(N, hi, hi, ci)
             else:
                 dx0 = dxin
-        for li, idx_ in enumerate((2, 4, 6, 8)):              # back to ConvTranspose2d layout (Cin,Cout,kh,kw)
-            wt = dec[idx_].weight
-            ci, co, kh, kw = wt.shape
-            src = gdec[li].view(kh, kw, copad[li], ci)[:, :, :co] if impl[li] else gdec[li].view(kh, kw, co, ci)
-            ops.permute4(src, G(wt), (3, 2, 0, 1))
-        ops.gemm(dx0, featN, G(dec[0].weight), a_mn=True, b_mn=True, accumulate=True)
-        ops.colsum(dx0, G(dec[0].bias))
+        with side():
+            for li, idx_ in enumerate((2, 4, 6, 8)):          # back to ConvTranspose2d layout (Cin,Cout,kh,kw)
+                wt = dec[idx_].weight
+                ci, co, kh, kw = wt.shape
+                src = gdec[li].view(kh, kw, copad[li], ci)[:, :, :co] if impl[li] else gdec[li].view(kh, kw, co, ci)
+                ops.permute4(src, G(wt), (3, 2, 0, 1))
+            ops.gemm(dx0, featN, G(dec[0].weight), a_mn=True, b_mn=True, accumulate=True)
+            ops.colsum(dx0, G(dec[0].bias))
         ops.gemm(dx0, W(dec[0].weight), dfeat, b_mn=True)                      # first writer of dfeat
 
         # ---- reward / terminal heads
@@ -986,6 +1064,61 @@ class Dreamer(nn.Module):
         if skinny:
             for buf_ in (dpin, dza, dhp, dhin, dzin):
                 ops.fill(buf_, 0.0)
+        # ---- encoder backward (as a function of an image-row range)
+        geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
+        encgw = {}
+
+        def enc_bwd_begin():
+            for li in (1, 2, 3):
+                _, _, ci, co = geo[li]
+                if self.implicit_conv:
+                    encgw[li] = b(f"bwd.gencwp{li}", co, 16 * ((ci + 31) // 32 * 32))   # channels padded to 32 per tap
+                else:
+                    encgw[li] = b(f"bwd.gencw{li}", co, 16 * ci)
+                ops.fill(encgw[li], 0.0)
+
+        def enc_bwd_rows(r0, r1):
+            n = r1 - r0
+            if I == 1:
+                dea_c = dy2.view(N, d.Hd)[r0:r1]
+            else:
+                dea_c = b("bwd.dea_c", NB, d.Hd)[r0:r1]
+                ops.group_sum(dy2.view(N, d.Hd)[r0 * I:r1 * I], I, dea_c)
+            dembed = b("bwd.dembed", NB, d.E)[r0:r1]
+            ops.gemm(dea_c, W(cell.post_mlp_e.weight), dembed, b_mn=True)
+            da = b("bwd.da3", NB * 4, 8 * cd)[r0 * 4:r1 * 4]
+            ops.permute4(dembed.view(n, 8 * cd, 4, 1), da.view(n, 4, 8 * cd, 1), (0, 2, 1, 3))
+            for li in (3, 2, 1, 0):
+                hin_, hout, ci, co = geo[li]
+                hw = hout * hout
+                act = b(f"enc.a{li}", NB * hw, co)[r0 * hw:r1 * hw]
+                ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
+                if li == 0:
+                    col = b(f"enc.col{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
+                    ops.gemm(da, col, G(enc[0].weight).view(co, 16 * ci), a_mn=True, b_mn=True, accumulate=True)
+                    continue
+                if self.implicit_conv:
+                    xprev = b(f"enc.a{li - 1}", NB * hin_ * hin_, ci)[r0 * hin_ * hin_:r1 * hin_ * hin_]
+                    ops.conv_gemm(3, xprev.view(n, hin_, hin_, ci), 4, da, encgw[li])
+                else:
+                    col = b(f"enc.col{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
+                    ops.gemm(da, col, encgw[li], a_mn=True, b_mn=True, accumulate=True)
+                dcol = b(f"bwd.dcol{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
+                ops.gemm(da, self._encw[li], dcol, b_mn=True)
+                da_prev = b(f"bwd.da{li - 1}", NB * hin_ * hin_, ci)[r0 * hin_ * hin_:r1 * hin_ * hin_]
+                ops.col2im(dcol, hout, hout, 4, None, ACT_NONE, da_prev.view(n, hin_, hin_, ci), round_out=False)
+                da = da_prev
+
+        def enc_bwd_end():
+            for li in (1, 2, 3):
+                _, _, ci, co = geo[li]
+                if self.implicit_conv:
+                    cpad = (ci + 31) // 32 * 32
+                    ops.permute4(encgw[li].view(co, 4, 4, cpad)[..., :ci], G(enc[2 * li].weight), (0, 3, 1, 2))
+                else:
+                    ops.permute4(encgw[li].view(co, 4, 4, ci), G(enc[2 * li].weight), (0, 3, 1, 2))
+
+        par = self._ov(2)
         for t in reversed(range(T)):
             nxt = t < T - 1
             ops.cat_st_bwd(post[t], d.G, d.C, dfeat3[t, :, d.D:], dzin[t + 1] if nxt else None,
@@ -994,13 +1127,21 @@ class Dreamer(nn.Module):
             ops.ln_elu_bwd(dpin[t], y2[t], pin[t], self._raw(cell.post_norm.weight), m2[t], r2[t], dy2[t],
                            G(cell.post_norm.weight), G(cell.post_norm.bias), G(cell.post_mlp_h.bias))
             ops.gemm(dy2[t], W(cell.post_mlp_h.weight), dhp[t], b_mn=True, res=dfeat3[t, :, :d.D], c_zeroed=skinny)
+            if par and nxt:
+                self._join(2)                       # dhin[t + 1]
             ops.gru_bwd(dhp[t], dhin[t + 1] if nxt else None, mask[t + 1] if nxt else None, gates[t], hin[t], dgi[t],
                         dgh[t], dhc)
-            ops.gemm(dgh[t], W(gru.weight_hh), dhin[t], b_mn=True, res=dhc, c_zeroed=skinny)
+            if par:
+                with self._fork(2):
+                    ops.gemm(dgh[t], W(gru.weight_hh), dhin[t], b_mn=True, res=dhc, c_zeroed=skinny)
+            else:
+                ops.gemm(dgh[t], W(gru.weight_hh), dhin[t], b_mn=True, res=dhc, c_zeroed=skinny)
             ops.gemm(dgi[t], W(gru.weight_ih), dza[t], b_mn=True, c_zeroed=skinny)
             ops.ln_elu_bwd(dza[t], x1[t], za[t], self._raw(cell.in_norm.weight), m1[t], r1[t], dx1[t],
                            G(cell.in_norm.weight), G(cell.in_norm.bias), G(cell.z_mlp.bias))
             ops.gemm(dx1[t], W(cell.z_mlp.weight), dzin[t], b_mn=True, c_zeroed=skinny)
+        if par:
+            self._join(2)
         # batched weight gradients over all T*BI rows
         f2 = lambda x: x.view(N, x.shape[-1])
         ops.gemm(f2(dpost), f2(pin), G(cell.post_mlp.weight), a_mn=True, b_mn=True, accumulate=True)
@@ -1019,39 +1160,11 @@ class Dreamer(nn.Module):
         embed = b("enc.embed", NB, d.E)
         ops.gemm(dea, embed, G(cell.post_mlp_e.weight), a_mn=True, b_mn=True, accumulate=True)
         ops.gemm(daa, obs["action"].reshape(NB, d.A), G(cell.a_mlp.weight), a_mn=True, b_mn=True, accumulate=True)
-        dembed = b("bwd.dembed", NB, d.E)
-        ops.gemm(dea, W(cell.post_mlp_e.weight), dembed, b_mn=True)
-
-        # ---- encoder backward
-        geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
-        da = b("bwd.da3", NB * 4, 8 * cd)
-        ops.permute4(dembed.view(NB, 8 * cd, 4, 1), da.view(NB, 4, 8 * cd, 1), (0, 2, 1, 3))
-        for li in (3, 2, 1, 0):
-            hin_, hout, ci, co = geo[li]
-            act = b(f"enc.a{li}", NB * hout * hout, co)
-            ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
-            if li == 0:
-                col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
-                ops.gemm(da, col, G(enc[0].weight).view(co, 16 * ci), a_mn=True, b_mn=True, accumulate=True)
-            else:
-                if self.implicit_conv:
-                    cpad = (ci + 31) // 32 * 32                   # (tap, channel) columns with channels padded to 32
-                    gw = b(f"bwd.gencwp{li}", co, 16 * cpad)
-                    ops.fill(gw, 0.0)
-                    xprev = b(f"enc.a{li - 1}", NB * hin_ * hin_, ci).view(NB, hin_, hin_, ci)
-                    ops.conv_gemm(3, xprev, 4, da, gw)
-                    ops.permute4(gw.view(co, 4, 4, cpad)[..., :ci], G(enc[2 * li].weight), (0, 3, 1, 2))
-                else:
-                    col = b(f"enc.col{li}", NB * hout * hout, 16 * ci)
-                    gw = b(f"bwd.gencw{li}", co, 16 * ci)
-                    ops.fill(gw, 0.0)
-                    ops.gemm(da, col, gw, a_mn=True, b_mn=True, accumulate=True)
-                    ops.permute4(gw.view(co, 4, 4, ci), G(enc[2 * li].weight), (0, 3, 1, 2))
-                dcol = b(f"bwd.dcol{li}", NB * hout * hout, 16 * ci)
-                ops.gemm(da, self._encw[li], dcol, b_mn=True)
-                da_prev = b(f"bwd.da{li - 1}", NB * hin_ * hin_, ci)
-                ops.col2im(dcol, hout, hout, 4, None, ACT_NONE, da_prev.view(NB, hin_, hin_, ci), round_out=False)
-                da = da_prev
+        enc_bwd_begin()
+        enc_bwd_rows(0, NB)
+        enc_bwd_end()
+        if par_w:
+            self._join(4)
 
     # ------------------------------------------------------------------ imagination rollout
     def _dream(self, feats, N, H, noise_actor, noise_prior, tag):
@@ -1074,6 +1187,14 @@ class Dreamer(nn.Module):
             ops.to_half(feats[0], f16b[0])
             za16, pp16 = b("dream.za16", N, d.Hd, dtype=torch.float16), b("dream.pp16", N, d.Hd, dtype=torch.float16)
             Wh = self._wh
+        par = self._ov(2)
+        if f16:
+            gh_gemm = lambda i: ops.gemm_f16(f16b[i][:, :d.D], Wh(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+        else:
+            gh_gemm = lambda i: ops.gemm(feats[i][:, :d.D], W(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+        if par:
+            with self._fork(2):
+                gh_gemm(0)
         for i in range(H):
             f, fn = feats[i], feats[i + 1]
             fh, fnh = (f16b[i], f16b[i + 1]) if f16 else (None, None)
@@ -1087,8 +1208,14 @@ class Dreamer(nn.Module):
                 ops.gemm_f16(fh[:, d.D:], Wh(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
                 ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr, za16)
                 ops.gemm_f16(za16, Wh(gru.weight_ih), gi, bias=self._raw(gru.bias_ih))
-                ops.gemm_f16(fh[:, :d.D], Wh(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+                if par:
+                    self._join(2)
+                else:
+                    gh_gemm(i)
                 ops.gru_fwd(gi, gh, f[:, :d.D], fn[:, :d.D], h16=fnh[:, :d.D])
+                if par and i + 1 < H:               # next step's h·W_hh overlaps prior MLP, sampling and the actor
+                    with self._fork(2):
+                        gh_gemm(i + 1)
                 ops.gemm_f16(fnh[:, :d.D], Wh(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
                 ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pp, mm, rr, pp16)
                 ops.gemm_f16(pp16, Wh(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
@@ -1097,8 +1224,14 @@ class Dreamer(nn.Module):
                 ops.gemm(f[:, d.D:], W(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
                 ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr)
                 ops.gemm(za, W(gru.weight_ih), gi, bias=self._raw(gru.bias_ih))
-                ops.gemm(f[:, :d.D], W(gru.weight_hh), gh, bias=self._raw(gru.bias_hh))
+                if par:
+                    self._join(2)
+                else:
+                    gh_gemm(i)
                 ops.gru_fwd(gi, gh, f[:, :d.D], fn[:, :d.D])
+                if par and i + 1 < H:
+                    with self._fork(2):
+                        gh_gemm(i + 1)
                 ops.gemm(fn[:, :d.D], W(cell.prior_mlp_h.weight), yp, bias=self._raw(cell.prior_mlp_h.bias))
                 ops.ln_elu_fwd(yp, self._raw(cell.prior_norm.weight), self._raw(cell.prior_norm.bias), 1e-3, pp, mm, rr)
                 ops.gemm(pp, W(cell.prior_mlp.weight), prior, bias=self._raw(cell.prior_mlp.bias))
