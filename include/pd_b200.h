@@ -130,6 +130,38 @@ int pd_cat_st_bwd(pd_handle* h, int M, int G, int C, const float* logits, long l
                   const float* extra, long ldex, const float* rowscale, float alpha,
                   float* dlogits, long lddl, void* stream);
 
+/* ---- persistent RSSM posterior unroll (rssm.py:21-78 RSSMCore.forward, 125-153 RSSMCell.forward) -------------
+ * ONE cooperative kernel walks all T timesteps: per step { z_mlp as a gather over the sampled one-hot + a_mlp term
+ * -> LayerNorm+ELU -> GRU gates (fp16 mma.sync tensor-core contractions, fp32 accumulate) -> post_mlp_h + embed term
+ * -> LayerNorm+ELU -> post_mlp -> categorical sample }, with grid-wide barriers between the dependent phases instead
+ * of kernel boundaries; every CTA owns a fixed slice of hidden units / features / latent groups for the whole
+ * sequence.  Writes exactly the buffers the chain of per-step kernels writes (the backward reads them).
+ * Caller prepares: hin[0] / zin[0] (masked in_state), x1[0] (pre-norm input of step 0 incl. bias and action term),
+ * aa / ea (action and embed projections hoisted over T), fp16 weight copies.  Limits: BI <= 64, Hd <= 1024,
+ * C <= 32, G <= #CTAs, D and Hd <= 16 * #CTAs and multiples of 8; otherwise PD_ERR_UNSUPPORTED (use the chain). */
+typedef struct pd_rssm_fwd_args {
+    int T, BI, I, D, Hd, G, C;                 /* rows BI = B*I; Z = G*C; feat row pitch F = D + Z */
+    const void *w_z16, *w_ih16, *w_hh16, *w_ph16, *w_pm16;   /* fp16 [Hd,Z] [3D,Hd] [3D,D] [Hd,D] [Z,Hd] */
+    const float *b_z, *ln1_g, *ln1_b, *b_ih, *b_hh, *b_ph, *ln2_g, *ln2_b, *b_pm;
+    float eps;
+    const float *aa;                           /* [T*B, Hd] */
+    const float *ea;                           /* [T*B, Hd] or NULL (open loop: no embed term) */
+    const float *mask;                         /* [T, BI]  1 - reset */
+    const float *noise;                        /* [T, BI, Z] Exp(1) */
+    float *x1, *za, *m1, *r1;                  /* [T,BI,Hd] x2, [T,BI] x2 */
+    float *gates;                              /* [T,BI,4D]  r,u,n,gh_n */
+    float *feat;                               /* [T,BI,D+Z] h' | z */
+    float *hin, *zin;                          /* [T,BI,D], [T,BI,Z] masked step inputs */
+    float *y2, *pin, *m2, *r2;                 /* [T,BI,Hd] x2, [T,BI] x2 */
+    float *post;                               /* [T,BI,Z] posterior logits */
+    int32_t *idx;                              /* [T,BI,G] sampled classes */
+    void *ws_wzT16;                            /* workspace fp16 [Z,Hd] */
+    void *ws_za16, *ws_h16, *ws_pin16;         /* workspace fp16 [BI,Hd] [BI,D] [BI,Hd] */
+    unsigned int *ws_barrier;                  /* workspace, 16 words, 8-byte aligned, cleared by the call: [0] barrier
+                                                * counter, [2..15] seven uint64 phase timers in ns (diagnostic) */
+} pd_rssm_fwd_args;
+int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
+
 /* ---- KL(post || prior) with balancing, entropies, unweighted grads ------------------------ */
 /* dreamer.py:328-343,369-379.  mode 0 (I == 1): value KL, grads (1-bal)*dKL/dpost and bal*dKL/dprior
  * (bal < 0 => plain KL, kl_balance == 0.5 case dreamer.py:241).  mode 1 (I > 1): sampled

@@ -695,6 +695,17 @@ class Dreamer(nn.Module):
     overlap = int(os.environ.get("PD_B200_OVERLAP", "3"))
     _scratch_ns = ""          # name space of the shared MLP scratch buffers (one per concurrent branch)
 
+    # PD_B200_PERSISTENT_RSSM=1: the posterior unroll runs as one cooperative kernel instead of 9 launches per timestep
+    persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "0") != "0"
+
+    def _persistent_rssm_ok(self, BI):
+        d = self.d
+        if not (self.persistent_rssm and self.fp16_forward and self._arena.is_cuda):
+            return False
+        P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count
+        return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and
+                d.G <= min(64, P) and -(-d.D // P) <= 16 and -(-d.Hd // P) <= 16)
+
     def _ov(self, bit):
         return bool(self.overlap & bit) and self._arena.is_cuda and self._phase_timer is None
 
@@ -795,13 +806,33 @@ class Dreamer(nn.Module):
         ops.mask_rows(in_state[0], mask[0], hin[0]); ops.mask_rows(in_state[1], mask[0], zin[0])
         x1, za = b("rssm.x1", T, BI, d.Hd), b("rssm.za", T, BI, d.Hd)
         m1, r1 = b("rssm.m1", T, BI), b("rssm.r1", T, BI)
-        gi, gh = b("rssm.gi", T, BI, 3 * d.D), b("rssm.gh", T, BI, 3 * d.D)
         gates = b("rssm.gates", T, BI, 4 * d.D)
         y2, pin = b("rssm.y2", T, BI, d.Hd), b("rssm.pin", T, BI, d.Hd)
         m2, r2 = b("rssm.m2", T, BI), b("rssm.r2", T, BI)
         post = b("rssm.post", T, BI, d.Z)
         idx = b("rssm.idx", T, BI, d.G, dtype=torch.int32)
         W = self._w
+        if self._persistent_rssm_ok(BI):
+            # one cooperative kernel for all T steps (csrc/pd_rssm_persistent.cu); step 0's pre-norm input is formed
+            # here because the incoming z need not be one-hot
+            Wh, h16 = self._wh, torch.float16
+            ops.gemm(zin[0], W(cell.z_mlp.weight), x1[0], bias=self._raw(cell.z_mlp.bias), res=aa[:B], r_div=I)
+            ph, pn, pm = ((cell.prior_mlp_h, cell.prior_norm, cell.prior_mlp) if open_loop else
+                          (cell.post_mlp_h, cell.post_norm, cell.post_mlp))
+            ops.rssm_unroll_fwd(
+                dict(T=T, BI=BI, I=I, D=d.D, Hd=d.Hd, G=d.G, C=d.C), 1e-3,
+                w_z16=Wh(cell.z_mlp.weight), w_ih16=Wh(gru.weight_ih), w_hh16=Wh(gru.weight_hh), w_ph16=Wh(ph.weight),
+                w_pm16=Wh(pm.weight), b_z=self._raw(cell.z_mlp.bias), ln1_g=self._raw(cell.in_norm.weight),
+                ln1_b=self._raw(cell.in_norm.bias), b_ih=self._raw(gru.bias_ih), b_hh=self._raw(gru.bias_hh),
+                b_ph=self._raw(ph.bias), ln2_g=self._raw(pn.weight), ln2_b=self._raw(pn.bias), b_pm=self._raw(pm.bias),
+                aa=aa, ea=None if open_loop else ea, mask=mask, noise=noise_post, x1=x1, za=za, m1=m1, r1=r1,
+                gates=gates, feat=feat, hin=hin, zin=zin, y2=y2, pin=pin, m2=m2, r2=r2, post=post, idx=idx,
+                ws_wzT16=b("k1.wzT", d.Z, d.Hd, dtype=h16), ws_za16=b("k1.za16", BI, d.Hd, dtype=h16),
+                ws_h16=b("k1.h16", BI, d.D, dtype=h16), ws_pin16=b("k1.pin16", BI, d.Hd, dtype=h16),
+                ws_barrier=b("k1.bar", 16, dtype=torch.int32))
+            out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
+            return img, post, idx, out_state
+        gi, gh = b("rssm.gi", T, BI, 3 * d.D), b("rssm.gh", T, BI, 3 * d.D)
         skinny = BI <= 128                      # the per-timestep GEMMs split K and reduce into C: clear all T slices at once
         if skinny:
             for buf_ in (x1, gi, gh, y2, post):

@@ -30,6 +30,17 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
+class RssmFwdArgs(ctypes.Structure):
+    """struct pd_rssm_fwd_args of include/pd_b200.h (same field order)."""
+    _INTS = ("T", "BI", "I", "D", "Hd", "G", "C")
+    _PTRS1 = ("w_z16", "w_ih16", "w_hh16", "w_ph16", "w_pm16", "b_z", "ln1_g", "ln1_b", "b_ih", "b_hh", "b_ph",
+              "ln2_g", "ln2_b", "b_pm")
+    _PTRS2 = ("aa", "ea", "mask", "noise", "x1", "za", "m1", "r1", "gates", "feat", "hin", "zin", "y2", "pin", "m2",
+              "r2", "post", "idx", "ws_wzT16", "ws_za16", "ws_h16", "ws_pin16", "ws_barrier")
+    _fields_ = ([(n, ctypes.c_int) for n in _INTS] + [(n, ctypes.c_void_p) for n in _PTRS1] +
+                [("eps", ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS2])
+
+
 class NativeOps:
     is_reference = False
 
@@ -158,6 +169,21 @@ class NativeOps:
                                      _ld(dh_b) if dh_b is not None else 0, _ptr(mask_b), _ptr(gates), _ptr(hprev),
                                      _ld(hprev), _ptr(dgi), _ld(dgi), _ptr(dgh), _ld(dgh), _ptr(dh_carry),
                                      _ld(dh_carry), self._s()), "pd_gru_bwd")
+
+    def rssm_unroll_fwd(self, dims, eps, **t):
+        """Persistent posterior unroll (pd_rssm_unroll_fwd).  dims = dict(T, BI, I, D, Hd, G, C); every other struct
+        field is passed as a contiguous tensor (or None) by its field name."""
+        a = RssmFwdArgs()
+        for n in RssmFwdArgs._INTS:
+            setattr(a, n, int(dims[n]))
+        a.eps = float(eps)
+        for n in RssmFwdArgs._PTRS1 + RssmFwdArgs._PTRS2:
+            v = t.pop(n, None)
+            if v is not None:
+                assert v.is_contiguous(), n
+                setattr(a, n, v.data_ptr())
+        assert not t, f"unknown fields {sorted(t)}"
+        self._ck(self.lib.pd_rssm_unroll_fwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd")
 
     def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]
