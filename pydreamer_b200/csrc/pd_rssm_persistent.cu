@@ -8,7 +8,7 @@
 // and 45 MB of fp16 weights.  Here every CTA keeps a fixed slice of the problem for all T steps
 //   * hidden units  [u0,u1)  of the GRU   (3 gate rows each, W_ih and W_hh)
 //   * features      [f0,f1)  of post_mlp_h
-//   * one latent group g (CTAs 0..G-1) of post_mlp + its categorical sample
+//   * one latent group g (CTAs 0..4G-1, four per group sharing the batch rows) of post_mlp + its categorical sample
 //   * one batch row b   (CTAs 0..BI-1) of the two LayerNorms and of the z_mlp gather
 // and the five dependent phases of a step are separated by grid barriers (one atomic + one polled word in L2).
 // Contractions: out[rows, batch] = W[rows, K] · X[batch, K]^T as mma.sync.m16n8k16 (fp16 operands, fp32 accumulate);
@@ -141,12 +141,11 @@ __device__ void contract(uint8_t* smem, const Tile (&tiles)[MT], const __half* X
             const bool kin = k0 + lane * 8 < K;
 #pragma unroll
             for (int i = 0; i < 2 * MT; ++i)
-                cp_async16(st + (warp + 8 * i) * ROWB, asrc[i] + (kin ? k0 : 0), kin && aval[i]);
+                if (aval[i]) cp_async16(st + (warp + 8 * i) * ROWB, asrc[i] + (kin ? k0 : 0), kin);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int b = warp + 8 * j;
-                const bool v = kin && b < BI;
-                cp_async16(st + (AROWS + b) * ROWB, X + (v ? (long)b * K + k0 + lane * 8 : 0), v);
+                if (b < BI) cp_async16(st + (AROWS + b) * ROWB, X + (long)b * K + (kin ? k0 + lane * 8 : 0), kin);
             }
         }
         cp_commit();
@@ -446,8 +445,11 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
         clk.lap(5);
 
         // ---- phase D (CTA g < G): logits of latent group g, softmax, argmax(p / q) -> post, idx, z
-        if (c < G) {
-            const int g = c;
+        // (R CTAs repeat the small contraction of a group and share its batch rows: the softmax / argmax chain is the
+        //  serial part of this phase)
+        const int R = max(1, min(4, P / G));
+        if (c < G * R) {
+            const int g = c / R, sub = c % R;
             Tile tiles[2];
             tiles[0].base = Wpm + (long)g * C * Hd;
             tiles[0].rows = C < 16 ? C : 16;
@@ -457,13 +459,14 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = warp + NW * i;
-                pq[i] = (lane < C && b < BI) ? a.noise[((long)t * BI + b) * Z + g * C + lane] : 1.f;
+                pq[i] = (lane < C && b < BI && i % R == sub) ? a.noise[((long)t * BI + b) * Z + g * C + lane] : 1.f;
             }
             contract<2>(smem, tiles, pin16, BI, Hd, red);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = warp + NW * i;
                 if (b >= BI) break;
+                if (i % R != sub) continue;
                 const long row = (long)t * BI + b;
                 const bool valid = lane < C;
                 float l = 0.f;

@@ -695,8 +695,9 @@ class Dreamer(nn.Module):
     overlap = int(os.environ.get("PD_B200_OVERLAP", "3"))
     _scratch_ns = ""          # name space of the shared MLP scratch buffers (one per concurrent branch)
 
-    # PD_B200_PERSISTENT_RSSM=1: the posterior unroll runs as one cooperative kernel instead of 9 launches per timestep
-    persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "0") != "0"
+    # The posterior unroll runs as ONE cooperative kernel (csrc/pd_rssm_persistent.cu) when the shape fits its limits
+    # (B*I <= 64 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
+    persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "1") != "0"
 
     def _persistent_rssm_ok(self, BI):
         d = self.d
