@@ -75,7 +75,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
         atomicAdd(ctr, 1u);
         unsigned spins = 0;
         while (ld_acquire(ctr) < target) {
-            if (++spins > (1u << 27)) __trap();          // a lost CTA must not hang the device
+            if (++spins > (1u << 24)) __trap();          // ~10 s: a lost CTA must not hang the device
         }
         __threadfence();
     }

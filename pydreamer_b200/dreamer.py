@@ -701,14 +701,16 @@ class Dreamer(nn.Module):
 
     def _persistent_rssm_ok(self, BI):
         d = self.d
-        if not (self.persistent_rssm and self.fp16_forward and self._arena.is_cuda):
-            return False
+        if not (self.persistent_rssm and self.fp16_forward and self._arena.is_cuda and self._dp is None):
+            return False                  # (data-parallel runs keep the per-step chain)
         P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count
         return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and
                 d.G <= min(64, P) and -(-d.D // P) <= 16 and -(-d.Hd // P) <= 16)
 
     def _ov(self, bit):
-        return bool(self.overlap & bit) and self._arena.is_cuda and self._phase_timer is None
+        # data-parallel runs keep the single-stream schedule (a 2-GPU run with side streams + the cooperative kernel did
+        # not complete, profiles/r01_h_2gpu_hang.err; not yet root-caused), so does the eager phase timer of bench.py
+        return bool(self.overlap & bit) and self._arena.is_cuda and self._phase_timer is None and self._dp is None
 
     def _side(self, k):
         key = (k, torch.cuda.current_stream(self._arena.device).cuda_stream)     # one side stream per (purpose, parent)
