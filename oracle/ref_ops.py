@@ -145,6 +145,57 @@ class RefOps:
         dgh.copy_(torch.cat([dr_pre, du_pre, dn_pre * r], 1))
         dh_carry.copy_(dh * u)
 
+    def rssm_unroll_fwd(self, dims, eps, **t):
+        """Torch statement of pd_rssm_unroll_fwd (csrc/pd_rssm_persistent.cu; rssm.py:21-78, 125-153): the whole posterior
+        unroll in one call, fp16 weights, LayerNorm outputs and h rounded to fp16 (they are the tensor-core operands)."""
+        T, BI, I, D, Hd, G, C = (int(dims[k]) for k in ("T", "BI", "I", "D", "Hd", "G", "C"))
+        B = BI // I
+        x1, za, m1, r1, gates, feat, hin, zin = (t[k] for k in ("x1", "za", "m1", "r1", "gates", "feat", "hin", "zin"))
+        y2, pin, m2, r2, post, idx = (t[k] for k in ("y2", "pin", "m2", "r2", "post", "idx"))
+        aa, ea, mask, noise = t["aa"], t.get("ea"), t["mask"], t["noise"]
+        dt = x1.dtype
+        Wz, Wih, Whh, Wph, Wpm = (t[k].to(dt) for k in ("w_z16", "w_ih16", "w_hh16", "w_ph16", "w_pm16"))
+        h16 = lambda v: v.to(torch.float16).to(dt)
+        rep = lambda v: v.repeat_interleave(I, 0) if I > 1 else v
+
+        def ln(x, g, b):
+            mu, var = x.mean(-1), x.var(-1, unbiased=False)
+            r = 1.0 / torch.sqrt(var + eps)
+            return h16(F.elu((x - mu[:, None]) * r[:, None] * g + b)), mu, r
+
+        gh = h16(hin[0]) @ Whh.t()                                       # raw product; mask and bias applied at use
+        for s in range(T):
+            m = mask[s] if s > 0 else torch.ones_like(mask[0])           # h_0 / z_0 arrive masked
+            if s > 0:
+                zprev = feat[s - 1][:, D:]
+                x1[s].copy_(m[:, None] * (zprev @ Wz.t()) + t["b_z"] + rep(aa[s * B:(s + 1) * B]))
+                zin[s].copy_(zprev * m[:, None])
+            y, mu, r = ln(x1[s], t["ln1_g"], t["ln1_b"])
+            za[s].copy_(y); m1[s].copy_(mu); r1[s].copy_(r)
+            gi = y @ Wih.t() + t["b_ih"]
+            ghb = m[:, None] * gh + t["b_hh"]
+            rg = torch.sigmoid(gi[:, :D] + ghb[:, :D])
+            ug = torch.sigmoid(gi[:, D:2 * D] + ghb[:, D:2 * D])
+            ghn = ghb[:, 2 * D:]
+            ng = torch.tanh(gi[:, 2 * D:] + rg * ghn)
+            hn = h16((1 - ug) * ng + ug * hin[s])
+            feat[s][:, :D].copy_(hn)
+            gates[s].view(BI, 4, D).copy_(torch.stack([rg, ug, ng, ghn], 1))
+            if s + 1 < T:
+                hin[s + 1].copy_(hn * mask[s + 1][:, None])
+            v = hn @ Wph.t() + t["b_ph"]
+            if ea is not None:
+                v = v + rep(ea[s * B:(s + 1) * B])
+            y2[s].copy_(v)
+            gh = hn @ Whh.t()
+            y, mu, r = ln(y2[s], t["ln2_g"], t["ln2_b"])
+            pin[s].copy_(y); m2[s].copy_(mu); r2[s].copy_(r)
+            post[s].copy_(y @ Wpm.t() + t["b_pm"])
+            _, p = _group_softmax(post[s], G, C)
+            k = (p / noise[s].reshape(BI, G, C)).argmax(-1)
+            idx[s].copy_(k.to(idx.dtype))
+            feat[s][:, D:].copy_(F.one_hot(k, C).to(dt).reshape(BI, G * C))
+
     def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]
         _, p = _group_softmax(logits, G, C)

@@ -701,9 +701,10 @@ class Dreamer(nn.Module):
 
     def _persistent_rssm_ok(self, BI):
         d = self.d
-        if not (self.persistent_rssm and self.fp16_forward and self._arena.is_cuda and self._dp is None):
+        on_gpu = self._arena.is_cuda
+        if not (self.persistent_rssm and self.fp16_forward and self._dp is None and (on_gpu or self.ops.is_reference)):
             return False                  # (data-parallel runs keep the per-step chain)
-        P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count
+        P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count if on_gpu else 148
         return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and
                 d.G <= min(64, P) and -(-d.D // P) <= 16 and -(-d.Hd // P) <= 16)
 

@@ -41,3 +41,34 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "UTCHMMA" in sass or "UTCMMA" in sass   # tcgen05.mma
     assert "UTMALDG" in sass                         # TMA tensor load
     assert "LDTM" in sass                            # tcgen05.ld
+
+
+def test_struct_argument_layout_matches_the_header(tmp_path):
+    """pd_rssm_fwd_args is the one struct in the ABI: the ctypes mirror (ops.RssmFwdArgs) must have the C compiler's
+    size and field offsets for the declaration in include/pd_b200.h."""
+    import os
+
+    from pydreamer_b200.ops import RssmFwdArgs
+
+    fields = [n for n, _ in RssmFwdArgs._fields_]
+    src = tmp_path / "layout.c"
+    body = "".join(f'    printf("{n} %zu\\n", offsetof(pd_rssm_fwd_args, {n}));\n' for n in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pd_b200.h"\nint main(void) {\n'
+                   '    printf("sizeof %zu\\n", sizeof(pd_rssm_fwd_args));\n' + body + "    return 0;\n}\n")
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.abspath(_native.HEADER)))
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)       # the header is plain C
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out.pop("sizeof")) == ctypes.sizeof(RssmFwdArgs)
+    assert list(out) == fields                                                      # same fields, same order
+    for n in fields:
+        assert int(out[n]) == getattr(RssmFwdArgs, n).offset, n
+
+
+def test_sass_of_the_persistent_rssm_kernel():
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "rssm_unroll_fwd_kernel", _native.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    if "HMMA" not in sass:                       # older cuobjdump: -fun wants the mangled name; fall back to the whole file
+        sass = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "HMMA.16816.F32" in sass              # mma.sync.m16n8k16 f16 -> f32
+    assert "LDGSTS" in sass and "LDSM" in sass   # cp.async staging, ldmatrix operand reads

@@ -20,10 +20,11 @@ def ref_ops():
     pd_ops.set_ops_for_testing(None)
 
 
-def run_model(case, fp16_forward=False):
+def run_model(case, fp16_forward=False, persistent_rssm=False):
     fx, conf, obs, state, noise = build_case(case)
     model = Dreamer(conf)
     model.fp16_forward = fp16_forward
+    model.persistent_rssm = persistent_rssm
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
     losses, out_state, metrics, tensors, dream = model.training_step(obs, state, noise=noise)
@@ -73,6 +74,22 @@ def test_fp16_forward_plumbing_stays_within_tolerance(ref_ops):
     for k, want in fx["grad_norms"].items():
         if k.startswith("wm."):                       # world-model gradients do not depend on the dream
             assert abs(float(named[k].grad.double().norm()) - want) <= 2e-4 * max(want, 1e-6) + 1e-9, k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_persistent_rssm_branch_of_the_schedule(ref_ops, case):
+    """The host branch that hands the whole posterior unroll to ONE call (pd_rssm_unroll_fwd on the GPU, its torch twin
+    here): same goldens; fp16-rounded operands in the recurrence move losses by < 2e-3 and may flip a near-tie sample."""
+    fx, conf, model, opts, losses, out_state, metrics, tensors = run_model(case, fp16_forward=True, persistent_rssm=True)
+    assert model._persistent_rssm_ok(conf.batch_size * conf.iwae_samples)
+    T, BI = conf.batch_length, conf.batch_size * conf.iwae_samples
+    assert ("rssm.gi", (T, BI, 3 * conf.deter_dim), torch.float32) not in model._ws      # the per-step chain did not run
+    for i, (got, want) in enumerate(zip(losses, fx["losses"])):
+        assert abs(float(got.detach().reshape(-1)[0]) - want) <= 5e-3 * max(1.0, abs(want)), (i, got, want)
+    named = dict(model.named_parameters())
+    for k, want in fx["grad_norms"].items():
+        if k.startswith("wm.") and want > 1e-6:
+            assert abs(float(named[k].grad.double().norm()) - want) <= 2e-2 * want + 1e-7, k
 
 
 def test_state_dict_roundtrip_and_grad_clip_and_optimizer(ref_ops):
