@@ -817,25 +817,31 @@ class Dreamer(nn.Module):
         idx = b("rssm.idx", T, BI, d.G, dtype=torch.int32)
         W = self._w
         if self._persistent_rssm_ok(BI):
-            # one cooperative kernel for all T steps (csrc/pd_rssm_persistent.cu); step 0's pre-norm input is formed
-            # here because the incoming z need not be one-hot
-            Wh, h16 = self._wh, torch.float16
-            ops.gemm(zin[0], W(cell.z_mlp.weight), x1[0], bias=self._raw(cell.z_mlp.bias), res=aa[:B], r_div=I)
-            ph, pn, pm = ((cell.prior_mlp_h, cell.prior_norm, cell.prior_mlp) if open_loop else
-                          (cell.post_mlp_h, cell.post_norm, cell.post_mlp))
-            ops.rssm_unroll_fwd(
-                dict(T=T, BI=BI, I=I, D=d.D, Hd=d.Hd, G=d.G, C=d.C), 1e-3,
-                w_z16=Wh(cell.z_mlp.weight), w_ih16=Wh(gru.weight_ih), w_hh16=Wh(gru.weight_hh), w_ph16=Wh(ph.weight),
-                w_pm16=Wh(pm.weight), b_z=self._raw(cell.z_mlp.bias), ln1_g=self._raw(cell.in_norm.weight),
-                ln1_b=self._raw(cell.in_norm.bias), b_ih=self._raw(gru.bias_ih), b_hh=self._raw(gru.bias_hh),
-                b_ph=self._raw(ph.bias), ln2_g=self._raw(pn.weight), ln2_b=self._raw(pn.bias), b_pm=self._raw(pm.bias),
-                aa=aa, ea=None if open_loop else ea, mask=mask, noise=noise_post, x1=x1, za=za, m1=m1, r1=r1,
-                gates=gates, feat=feat, hin=hin, zin=zin, y2=y2, pin=pin, m2=m2, r2=r2, post=post, idx=idx,
-                ws_wzT16=b("k1.wzT", d.Z, d.Hd, dtype=h16), ws_za16=b("k1.za16", BI, d.Hd, dtype=h16),
-                ws_h16=b("k1.h16", BI, d.D, dtype=h16), ws_pin16=b("k1.pin16", BI, d.Hd, dtype=h16),
-                ws_barrier=b("k1.bar", 16, dtype=torch.int32))
-            out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
-            return img, post, idx, out_state
+            try:
+                # one cooperative kernel for all T steps (csrc/pd_rssm_persistent.cu); step 0's pre-norm input is formed
+                # here because the incoming z need not be one-hot
+                Wh, h16 = self._wh, torch.float16
+                ops.gemm(zin[0], W(cell.z_mlp.weight), x1[0], bias=self._raw(cell.z_mlp.bias), res=aa[:B], r_div=I)
+                ph, pn, pm = ((cell.prior_mlp_h, cell.prior_norm, cell.prior_mlp) if open_loop else
+                              (cell.post_mlp_h, cell.post_norm, cell.post_mlp))
+                ops.rssm_unroll_fwd(
+                    dict(T=T, BI=BI, I=I, D=d.D, Hd=d.Hd, G=d.G, C=d.C), 1e-3,
+                    w_z16=Wh(cell.z_mlp.weight), w_ih16=Wh(gru.weight_ih), w_hh16=Wh(gru.weight_hh), w_ph16=Wh(ph.weight),
+                    w_pm16=Wh(pm.weight), b_z=self._raw(cell.z_mlp.bias), ln1_g=self._raw(cell.in_norm.weight),
+                    ln1_b=self._raw(cell.in_norm.bias), b_ih=self._raw(gru.bias_ih), b_hh=self._raw(gru.bias_hh),
+                    b_ph=self._raw(ph.bias), ln2_g=self._raw(pn.weight), ln2_b=self._raw(pn.bias), b_pm=self._raw(pm.bias),
+                    aa=aa, ea=None if open_loop else ea, mask=mask, noise=noise_post, x1=x1, za=za, m1=m1, r1=r1,
+                    gates=gates, feat=feat, hin=hin, zin=zin, y2=y2, pin=pin, m2=m2, r2=r2, post=post, idx=idx,
+                    ws_wzT16=b("k1.wzT", d.Z, d.Hd, dtype=h16), ws_za16=b("k1.za16", BI, d.Hd, dtype=h16),
+                    ws_h16=b("k1.h16", BI, d.D, dtype=h16), ws_pin16=b("k1.pin16", BI, d.Hd, dtype=h16),
+                    ws_barrier=b("k1.bar", 16, dtype=torch.int32))
+                out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
+                return img, post, idx, out_state
+            except RuntimeError as e:        # e.g. cooperative launch refused (SMs reserved by MPS / green contexts)
+                import warnings
+                warnings.warn(f"pydreamer_b200: persistent RSSM kernel unavailable ({e}); using the per-timestep chain")
+                self.persistent_rssm = False
+
         gi, gh = b("rssm.gi", T, BI, 3 * d.D), b("rssm.gh", T, BI, 3 * d.D)
         skinny = BI <= 128                      # the per-timestep GEMMs split K and reduce into C: clear all T slices at once
         if skinny:
