@@ -48,6 +48,26 @@ class Learner:
         metrics.update(grad_metrics)
         return metrics, tensors, dream
 
+    def train_on_episodes(self, directory, num_steps, skip_first=True):
+        """Gradient steps straight from a directory of the reference's episode `.npz` files (episodes.py): raw uint8 /
+        integer batches cross PCIe and are converted on the device (preprocess.py).  train.py:104-131,146-166 without
+        the DataLoader workers.  Returns the metrics of the last step."""
+        from .episodes import EpisodeDirectory, SequentialBatches
+        from .preprocess import GpuPreprocessor
+
+        conf = self.conf
+        batches = SequentialBatches(EpisodeDirectory(directory), conf.batch_length, conf.batch_size, skip_first=skip_first,
+                                    reset_interval=getattr(conf, "reset_interval", 0),
+                                    buffer_size=getattr(conf, "buffer_size", 0),
+                                    allow_mid_reset=getattr(conf, "allow_mid_reset", False))
+        pre = GpuPreprocessor(conf, self.device)
+        keys = ("image", "action", "reward", "terminal", "reset")
+        metrics = None
+        for _, raw in zip(range(num_steps), batches):
+            obs = pre.apply({k: raw[k] for k in keys if k in raw})
+            metrics, _, _ = self.step(obs)
+        return metrics
+
     # ---- tools.py:164-197
     def save_checkpoint(self, path):
         ck = {"epoch": self.steps, "model_state_dict": {k: v.detach().cpu() for k, v in self.model.state_dict().items()}}
