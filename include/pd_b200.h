@@ -161,6 +161,8 @@ typedef struct pd_rssm_fwd_args {
                                                 * counter, [2..15] seven uint64 phase timers in ns (diagnostic) */
 } pd_rssm_fwd_args;
 int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
+/* Work in progress (not yet run on a GPU): same contract, operands staged as 2-D TMA tiles when PD_B200_K1_STAGING=tma. */
+int pd_rssm_unroll_fwd_v2(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
 
 /* ---- KL(post || prior) with balancing, entropies, unweighted grads ------------------------ */
 /* dreamer.py:328-343,369-379.  mode 0 (I == 1): value KL, grads (1-bal)*dKL/dpost and bal*dKL/dprior

@@ -1,4 +1,7 @@
-// pd_rssm_persistent.cu — the posterior unroll of the RSSM as ONE cooperative kernel (pd_rssm_unroll_fwd).
+// pd_rssm_persistent_v2.cu — WORK IN PROGRESS copy of pd_rssm_persistent.cu that adds 2-D TMA tile staging
+// (PD_B200_K1_STAGING=tma).  Written after the round's GPU budget was spent: compiled, never executed on a GPU.  It is a
+// separate translation unit / entry point (pd_rssm_unroll_fwd_v2) so that the validated kernel stays byte-identical;
+// once measured it replaces the original.  Everything below the staging code is the same as in pd_rssm_persistent.cu.
 //
 // Reference semantics: pydreamer/models/rssm.py:21-78 (RSSMCore.forward time loop) and :125-153
 // (RSSMCell.forward: z_mlp + a_mlp -> in_norm -> ELU -> GRUCell -> post_mlp_h + post_mlp_e -> post_norm -> ELU ->
@@ -18,6 +21,7 @@
 // stores + __threadfence, read with cp.async.cg / ld.global.cg, never through L1).
 #include "pd_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -37,7 +41,8 @@ constexpr int OFF_SH = SMEM_MAIN;              // 64 floats: block reductions
 constexpr int OFF_SIDX = OFF_SH + 256;        // 64 ints: sampled classes of one row
 constexpr int OFF_GH = OFF_SIDX + 256;        // [3][16][BROWS] floats: h·W_hh^T of my units (lives across phases)
 constexpr int OFF_HC = OFF_GH + 3 * 16 * BROWS * 4;   // [16][BROWS] floats: masked h of my units, input of the next step
-constexpr int SMEM_BYTES = OFF_HC + 16 * BROWS * 4;
+constexpr int OFF_BAR = OFF_HC + 16 * BROWS * 4;      // STAGES mbarriers of the TMA staging
+constexpr int SMEM_BYTES = OFF_BAR + 64;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,6 +71,7 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 }
 
 // Grid-wide barrier on a monotonically increasing counter (cleared by the host before the launch).
+template <bool ASYNC_PROXY = false>
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -80,6 +86,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
         __threadfence();
     }
     __syncthreads();
+    if (ASYNC_PROXY) asm volatile("fence.proxy.async;" ::: "memory");   // TMA reads after the barrier see what it published
 }
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -197,6 +204,137 @@ __device__ void contract(uint8_t* smem, const Tile (&tiles)[MT], const __half* X
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Alternative staging (PD_B200_K1_STAGING=tma): operands arrive as 2-D TMA tiles (tensor maps over the fp16 matrices,
+// 128-byte swizzle) - ~20 copy-engine operations per 256-wide K chunk instead of 128 warp-wide LDGSTS, which leaves the
+// LSU to ldmatrix.  Out-of-range rows / K tail are zero-filled by the copy engine.  Stage layout per 64-wide k-block:
+// [MAXMT weight tiles of 16 rows x 128 B][64 activation rows x 128 B], every box 1024-byte aligned.
+// ---------------------------------------------------------------------------------------------------------------
+struct K1Maps {
+    CUtensorMap wih, whh, wph, wpm;      // weights: box {64 halfs, 16 rows}
+    CUtensorMap za, h, pin;              // activations: box {64 halfs, 64 rows}
+};
+
+constexpr int KB = 64;                                   // halfs per k-block (= one 128-byte swizzle row)
+constexpr int KBLK_BYTES = MAXMT * 16 * 128 + BROWS * 128;    // 16 KB
+constexpr int TSTAGE_BYTES = (KC / KB) * KBLK_BYTES;     // 64 KB
+static_assert(STAGES * TSTAGE_BYTES <= SMEM_MAIN, "TMA stages must fit the staging region");
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(s_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_tile(const CUtensorMap* map, uint64_t* bar, void* dst, int k, int row) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s_u32(dst)), "l"((uint64_t)map), "r"(s_u32(bar)), "r"(k), "r"(row) : "memory");
+}
+
+struct TileT {                 // one m16 tile of weight rows out of a tensor map; rows == 0: not needed in this call
+    const CUtensorMap* map;
+    int row0, rows;
+};
+struct Pipe {                  // chunks staged so far over the whole kernel: stage = n % STAGES, parity = (n / STAGES) & 1
+    uint64_t* full;
+    uint32_t n;
+};
+
+template <int MT>
+__device__ void contract_tma(uint8_t* smem, Pipe& pipe, const TileT (&tiles)[MT], const CUtensorMap* xmap, int BI, int K,
+                             float* red) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = (K + KC - 1) / KC;
+    const int ntile8 = (BI + 7) >> 3;
+    float acc[MT][8][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    int nt = 0;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) nt += tiles[i].rows > 0;
+
+    auto issue = [&](int chunk) {
+        if (tid == 0 && chunk < nchunks) {
+            const uint32_t n = pipe.n + chunk;
+            uint64_t* bar = pipe.full + n % STAGES;
+            uint8_t* st = smem + (n % STAGES) * TSTAGE_BYTES;
+            const int k0 = chunk * KC;
+            const int nkb = min(KC / KB, (K - k0 + KB - 1) / KB);          // k-blocks that intersect [0, K)
+            mbar_expect_tx(bar, (uint32_t)nkb * (uint32_t)(nt * 16 * 128 + BROWS * 128));
+            for (int kb = 0; kb < nkb; ++kb) {
+                uint8_t* blk = st + kb * KBLK_BYTES;
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+                    if (tiles[i].rows > 0) tma_tile(tiles[i].map, bar, blk + i * 2048, k0 + kb * KB, tiles[i].row0);
+                tma_tile(xmap, bar, blk + MAXMT * 2048, k0 + kb * KB, 0);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; ++i) issue(i);
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t n = pipe.n + c;
+        mbar_wait(pipe.full + n % STAGES, (n / STAGES) & 1);    // chunk c has landed
+        __syncthreads();                                        // chunk c-1 is fully consumed by every warp
+        issue(c + STAGES - 1);                                  // refills the stage chunk c-1 used
+        const uint8_t* st = smem + (n % STAGES) * TSTAGE_BYTES;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int ks = warp + 8 * half;                     // 16-wide k-step of the chunk: k-block ks/4, step ks%4
+            if (c * KC + ks * 16 < K) {
+                const uint8_t* blk = st + (ks >> 2) * KBLK_BYTES;
+                const int kl = ks & 3;
+                uint32_t a[MT][4];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    const int r = lane & 15;
+                    ldsm_x4(s_u32(blk + i * 2048 + r * 128 + (((kl * 2 + (lane >> 4)) ^ (r & 7)) << 4)), a[i][0], a[i][1],
+                            a[i][2], a[i][3]);
+                }
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    if (jp * 2 < ntile8) {
+                        uint32_t b0, b1, b2, b3;
+                        const int nrow = (jp * 2 + (lane >> 4)) * 8 + (lane & 7);
+                        ldsm_x4(s_u32(blk + MAXMT * 2048 + nrow * 128 + (((kl * 2 + ((lane >> 3) & 1)) ^ (lane & 7)) << 4)),
+                                b0, b1, b2, b3);
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) {
+                            mma16816(acc[i][jp * 2], a[i], b0, b1);
+                            if (jp * 2 + 1 < ntile8) mma16816(acc[i][jp * 2 + 1], a[i], b2, b3);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    pipe.n += nchunks;
+    __syncthreads();                                            // red aliases the staging buffers (all tiles have landed)
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float* r0 = red + ((warp * MAXMT + i) * 16 + gq) * REDP + j * 8 + tq * 2;
+            r0[0] = acc[i][j][0]; r0[1] = acc[i][j][1];
+            r0[8 * REDP] = acc[i][j][2]; r0[8 * REDP + 1] = acc[i][j][3];
+        }
+    __syncthreads();
+}
+
 __device__ __forceinline__ float red_sum(const float* red, int tile, int r, int b) {
     float s = 0.f;
 #pragma unroll
@@ -232,9 +370,11 @@ __device__ void ln_elu_row(float (&v)[4], int N, const float* __restrict__ gamma
     if (threadIdx.x == 0) { *mean_out = mean; *rstd_out = rstd; }
 }
 
-__global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fwd_args a) {
+template <bool TMA>
+__global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fwd_args a, const __grid_constant__ K1Maps maps) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    constexpr uintptr_t AL = TMA ? 1023 : 127;                 // swizzled TMA boxes need 1024-byte alignment
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + AL) & ~AL);
     float* red = (float*)smem;
     float* sh = (float*)(smem + OFF_SH);
     int* sidx = (int*)(smem + OFF_SIDX);
@@ -257,6 +397,16 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
     __half* h16 = (__half*)a.ws_h16;
     __half* pin16 = (__half*)a.ws_pin16;
     unsigned epoch = 0;
+    Pipe pipe;
+    pipe.full = (uint64_t*)(smem + OFF_BAR);
+    pipe.n = 0;
+    if (TMA) {
+        if (tid == 0) {
+            for (int i = 0; i < STAGES; ++i) mbar_init(pipe.full + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     PhaseClock clk;
     clk.start(a.ws_barrier);
 
@@ -276,7 +426,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
         for (long i = (long)c * NT + tid; i < (long)BI * D; i += (long)P * NT) h16[i] = __float2half_rn(__ldcg(a.hin + i));
         for (int o = tid; o < nu * BI; o += NT) hcs[(o % nu) * BROWS + o / nu] = __ldcg(a.hin + (long)(o / nu) * D + u0 + o % nu);
     }
-    grid_barrier(a.ws_barrier, epoch);
+    grid_barrier<TMA>(a.ws_barrier, epoch);
     clk.lap(0);
 
     // gh_0 = h_0 · W_hh^T (raw product; bias and the step mask are applied where it is consumed)
@@ -296,7 +446,15 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
                 pea[i] = a.b_ph[f] + (a.ea ? a.ea[((long)t * Bq + b / a.I) * Hd + f] : 0.f);
             }
         }
-        contract<4>(smem, tiles, h16, BI, D, red);
+        if constexpr (TMA) {
+            TileT tt[4];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) { tt[g].map = &maps.whh; tt[g].row0 = g * D + u0; tt[g].rows = tiles[g].rows; }
+            tt[3].map = &maps.wph; tt[3].row0 = f0; tt[3].rows = tiles[3].rows;
+            contract_tma<4>(smem, pipe, tt, &maps.h, BI, D, red);
+        } else {
+            contract<4>(smem, tiles, h16, BI, D, red);
+        }
         if (want_gh)
             for (int o = tid; o < 3 * nu * BI; o += NT) {
                 const int r = o % nu, b = (o / nu) % BI, g = o / (nu * BI);
@@ -314,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
         }
     };
     phase_hidden(0, true, false);
-    grid_barrier(a.ws_barrier, epoch);
+    grid_barrier<TMA>(a.ws_barrier, epoch);
     clk.lap(1);
 
     for (int t = 0; t < T; ++t) {
@@ -376,7 +534,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
             }
             ln_elu_row(v, Hd, a.ln1_g, a.ln1_b, a.eps, a.za + row * Hd, za16 + (long)b * Hd, a.m1 + row, a.r1 + row, sh);
         }
-        grid_barrier(a.ws_barrier, epoch);
+        grid_barrier<TMA>(a.ws_barrier, epoch);
         clk.lap(2);
 
         // ---- phase B (all CTAs): gi = za · W_ih^T for my units, GRU gate math, h' -> feat / hin[t+1] / h16
@@ -395,7 +553,14 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
                     if (t + 1 < T) pmn[i] = a.mask[row + BI];
                 }
             }
-            contract<3>(smem, tiles, za16, BI, Hd, red);
+            if constexpr (TMA) {
+                TileT tt[3];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) { tt[g].map = &maps.wih; tt[g].row0 = g * D + u0; tt[g].rows = nu; }
+                contract_tma<3>(smem, pipe, tt, &maps.za, BI, Hd, red);
+            } else {
+                contract<3>(smem, tiles, za16, BI, Hd, red);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int o = tid + NT * i;
@@ -421,12 +586,12 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
                 }
             }
         }
-        grid_barrier(a.ws_barrier, epoch);
+        grid_barrier<TMA>(a.ws_barrier, epoch);
         clk.lap(3);
 
         // ---- phase C (all CTAs): y2 = h' · W_ph^T + b + ea_t for my features; gh_{t+1} = h' · W_hh^T for my units
         phase_hidden(t, t + 1 < T, true);
-        grid_barrier(a.ws_barrier, epoch);
+        grid_barrier<TMA>(a.ws_barrier, epoch);
         clk.lap(4);
 
         // ---- phase C' (CTA b < BI): LayerNorm + ELU of y2 -> pin
@@ -441,7 +606,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
             }
             ln_elu_row(v, Hd, a.ln2_g, a.ln2_b, a.eps, a.pin + row * Hd, pin16 + (long)b * Hd, a.m2 + row, a.r2 + row, sh);
         }
-        grid_barrier(a.ws_barrier, epoch);
+        grid_barrier<TMA>(a.ws_barrier, epoch);
         clk.lap(5);
 
         // ---- phase D (CTA g < G): logits of latent group g, softmax, argmax(p / q) -> post, idx, z
@@ -461,7 +626,14 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
                 const int b = warp + NW * i;
                 pq[i] = (lane < C && b < BI && i % R == sub) ? a.noise[((long)t * BI + b) * Z + g * C + lane] : 1.f;
             }
-            contract<2>(smem, tiles, pin16, BI, Hd, red);
+            if constexpr (TMA) {
+                TileT tt[2];
+                tt[0].map = &maps.wpm; tt[0].row0 = g * C; tt[0].rows = tiles[0].rows;
+                tt[1].map = &maps.wpm; tt[1].row0 = g * C + 16; tt[1].rows = tiles[1].rows;
+                contract_tma<2>(smem, pipe, tt, &maps.pin, BI, Hd, red);
+            } else {
+                contract<2>(smem, tiles, pin16, BI, Hd, red);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = warp + NW * i;
@@ -495,42 +667,74 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
                 if (lane == 0) a.idx[row * G + g] = k;
             }
         }
-        if (t + 1 < T) grid_barrier(a.ws_barrier, epoch);
+        if (t + 1 < T) grid_barrier<TMA>(a.ws_barrier, epoch);
         clk.lap(6);
     }
 }
 
 }  // namespace
 
-extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp16 matrix [rows, K] (row-major) as a 2-D tensor map with boxes of 64 halfs x box_rows, 128-byte swizzle, zero OOB fill
+static int k1_map(pd_handle* h, CUtensorMap* tm, const void* base, int rows, int K, int box_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, gdim, gstride, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "pd_rssm_unroll_fwd_v2: cuTensorMapEncodeTiled failed (%d) for [%d, %d]", (int)r, rows, K);
+    return PD_OK;
+}
+
+extern "C" int pd_rssm_unroll_fwd_v2(pd_handle* h, const pd_rssm_fwd_args* a, void* stream) {
     if (!h || !a) return PD_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    static int configured = 0, max_ctas = 0;
+    static int configured = 0, max_ctas = 0, use_tma = 0;
+    constexpr size_t SMEM_REQ = (size_t)SMEM_BYTES + 1024;
     if (!configured) {
-        if (cudaFuncSetAttribute(rssm_unroll_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 128) !=
-            cudaSuccess)
-            PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: cannot reserve %d bytes of shared memory", SMEM_BYTES);
+        const char* e = getenv("PD_B200_K1_STAGING");          // "tma": 2-D tensor-map tiles; default: cp.async rows
+        use_tma = e && !strcmp(e, "tma") && h->encode_tiled;
+        if (cudaFuncSetAttribute(rssm_unroll_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_REQ) != cudaSuccess ||
+            cudaFuncSetAttribute(rssm_unroll_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_REQ) != cudaSuccess)
+            PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd_v2: cannot reserve %d bytes of shared memory", (int)SMEM_REQ);
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rssm_unroll_fwd_kernel, NT, SMEM_BYTES + 128);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rssm_unroll_fwd_kernel<false>, NT, SMEM_REQ);
         max_ctas = per_sm > 0 ? h->num_sms : 0;               // one CTA per SM
         configured = 1;
     }
     const int P = max_ctas;
-    PD_REQUIRE(h, P > 0, "pd_rssm_unroll_fwd: kernel does not fit an SM");
+    PD_REQUIRE(h, P > 0, "pd_rssm_unroll_fwd_v2: kernel does not fit an SM");
     const int Z = a->G * a->C;
     const bool ok = a->T >= 1 && a->BI >= 1 && a->BI <= BROWS && a->BI <= P && a->I >= 1 && a->BI % a->I == 0 &&
                     a->Hd <= 4 * NT && a->Hd % 8 == 0 && a->D % 8 == 0 && a->C >= 1 && a->C <= 32 && a->G >= 1 &&
                     a->G <= P && a->G <= 64 && (a->D + P - 1) / P <= 16 && (a->Hd + P - 1) / P <= 16 && Z >= 1;
     if (!ok)
-        PD_FAIL(h, PD_ERR_UNSUPPORTED, "pd_rssm_unroll_fwd: shape T=%d BI=%d D=%d Hd=%d G=%d C=%d outside the kernel's limits",
+        PD_FAIL(h, PD_ERR_UNSUPPORTED, "pd_rssm_unroll_fwd_v2: shape T=%d BI=%d D=%d Hd=%d G=%d C=%d outside the kernel's limits",
                 a->T, a->BI, a->D, a->Hd, a->G, a->C);
     if (cudaMemsetAsync(a->ws_barrier, 0, 16 * sizeof(unsigned), s) != cudaSuccess)
-        PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: memset failed");
+        PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd_v2: memset failed");
     pd_rssm_fwd_args args = *a;
-    void* kargs[] = {(void*)&args};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)rssm_unroll_fwd_kernel, dim3(P), dim3(NT), kargs,
-                                                (size_t)SMEM_BYTES + 128, s);
-    if (e != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: %s", cudaGetErrorString(e));
-    PD_CHECK_LAUNCH(h, "pd_rssm_unroll_fwd");
+    K1Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (use_tma) {
+        int rc = k1_map(h, &maps.wih, a->w_ih16, 3 * a->D, a->Hd, 16);
+        if (!rc) rc = k1_map(h, &maps.whh, a->w_hh16, 3 * a->D, a->D, 16);
+        if (!rc) rc = k1_map(h, &maps.wph, a->w_ph16, a->Hd, a->D, 16);
+        if (!rc) rc = k1_map(h, &maps.wpm, a->w_pm16, Z, a->Hd, 16);
+        if (!rc) rc = k1_map(h, &maps.za, a->ws_za16, a->BI, a->Hd, BROWS);
+        if (!rc) rc = k1_map(h, &maps.h, a->ws_h16, a->BI, a->D, BROWS);
+        if (!rc) rc = k1_map(h, &maps.pin, a->ws_pin16, a->BI, a->Hd, BROWS);
+        if (rc) return rc;
+    }
+    void* kargs[] = {(void*)&args, (void*)&maps};
+    const void* fn = use_tma ? (const void*)rssm_unroll_fwd_kernel<true> : (const void*)rssm_unroll_fwd_kernel<false>;
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(P), dim3(NT), kargs, SMEM_REQ, s);
+    if (e != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd_v2: %s", cudaGetErrorString(e));
+    PD_CHECK_LAUNCH(h, "pd_rssm_unroll_fwd_v2");
     return PD_OK;
 }

@@ -190,7 +190,10 @@ class NativeOps:
                 assert v.is_contiguous(), n
                 setattr(a, n, v.data_ptr())
         assert not t, f"unknown fields {sorted(t)}"
-        self._ck(self.lib.pd_rssm_unroll_fwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd")
+        if os.environ.get("PD_B200_K1_STAGING", "") == "tma":     # work-in-progress kernel (csrc/pd_rssm_persistent_v2.cu)
+            self._ck(self.lib.pd_rssm_unroll_fwd_v2(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd_v2")
+        else:
+            self._ck(self.lib.pd_rssm_unroll_fwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd")
 
     def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]
