@@ -270,6 +270,10 @@ int pd_sumsq(pd_handle* h, const float* x, long n, float* out /* += */, void* st
 /* norm = sqrt(*sumsq); coef = min(1, max_norm/(norm+1e-6)); x *= coef; *norm_out = norm
  * (== torch.nn.utils.clip_grad_norm_). */
 int pd_clip_scale(pd_handle* h, float* x, long n, const float* sumsq, float max_norm, float* norm_out, void* stream);
+/* x *= alpha * (*scale) without operand rounding (scale may be NULL = 1); exits without touching memory when the factor is
+ * exactly 1.  Applies the grad_output of `loss.backward(g)` (train.py:184-187, GradScaler under amp) and the 1/world of the
+ * data-parallel mean to the gradient arena. */
+int pd_scale_by(pd_handle* h, float* x, long n, const float* scale, float alpha, void* stream);
 /* torch.optim.AdamW (decoupled wd, no amsgrad); *step is a device int32 already incremented. */
 int pd_adamw(pd_handle* h, float* p, const float* g, float* m, float* v, long n,
              float lr, float beta1, float beta2, float eps, float wd, const int32_t* step, void* stream);

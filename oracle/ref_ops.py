@@ -310,6 +310,9 @@ class RefOps:
         rows = torch.arange(x.shape[0], device=x.device) // scale_div
         x.mul_(alpha * scale[rows][:, None])
 
+    def scale_by(self, x, scale=None, alpha=1.0):
+        x.mul_(alpha * (scale.reshape(-1)[0] if scale is not None else 1.0))
+
     def group_sum(self, x, I, out):
         R, W = out.shape
         out.copy_(x[:, :W].reshape(R, I, W).sum(1))

@@ -25,6 +25,25 @@ struct pd_handle {
     int gemm_2cta;            // allow the cta_group::2 256x256 kernel for large problems
     int gemm2_smem_configured;
     int round_ops;            // round tensor-core operands to tf32 (rna) where they are produced
+    int k1_configured;        // persistent RSSM kernels: shared-memory opt-in done on THIS handle's device
+    int k1_ctas;              // ... and the co-resident grid they launch (one CTA per SM)
+    int k1b_configured;
+    int k1b_ctas;
+};
+
+// Launch wrappers run on the handle's device whatever the caller's current device is (and put it back).
+struct PdDeviceGuard {
+    int prev;
+    bool switched;
+    explicit PdDeviceGuard(const pd_handle* h) : prev(-1), switched(false) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) {
+            cudaSetDevice(h->device);
+            switched = true;
+        }
+    }
+    ~PdDeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
 };
 
 #define PD_FAIL(h, code, ...)                                        \

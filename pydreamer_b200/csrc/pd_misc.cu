@@ -352,6 +352,13 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 __global__ void inc_kernel(int32_t* c) { *c += 1; }
+// x *= alpha * (*scale), exact (no operand rounding); a factor of exactly 1 leaves x untouched, so the launch exits
+// without touching memory (the usual loss.backward() hands over grad_output == 1)
+__global__ void scale_by_kernel(float* __restrict__ x, long n, const float* __restrict__ scale, float alpha) {
+    const float f = alpha * (scale ? *scale : 1.f);
+    if (f == 1.f) return;
+    GRID_STRIDE(i, n) x[i] *= f;
+}
 
 }  // namespace
 
@@ -476,6 +483,11 @@ int pd_adamw(pd_handle* h, float* p, const float* g, float* m, float* v, long n,
              float eps, float wd, const int32_t* step, void* stream) {
     adamw_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, step);
     PD_CHECK_LAUNCH(h, "adamw");
+    return PD_OK;
+}
+int pd_scale_by(pd_handle* h, float* x, long n, const float* scale, float alpha, void* stream) {
+    scale_by_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, S(stream)>>>(x, n, scale, alpha);
+    PD_CHECK_LAUNCH(h, "scale_by");
     return PD_OK;
 }
 int pd_inc(pd_handle* h, int32_t* counter, void* stream) {

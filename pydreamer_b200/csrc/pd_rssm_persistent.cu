@@ -505,17 +505,17 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd_kernel(const pd_rssm_fw
 extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream) {
     if (!h || !a) return PD_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    static int configured = 0, max_ctas = 0;
-    if (!configured) {
+    PdDeviceGuard guard(h);
+    if (!h->k1_configured) {                                   // per handle = per device (the attribute is per device)
         if (cudaFuncSetAttribute(rssm_unroll_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 128) !=
             cudaSuccess)
             PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: cannot reserve %d bytes of shared memory", SMEM_BYTES);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rssm_unroll_fwd_kernel, NT, SMEM_BYTES + 128);
-        max_ctas = per_sm > 0 ? h->num_sms : 0;               // one CTA per SM
-        configured = 1;
+        h->k1_ctas = per_sm > 0 ? h->num_sms : 0;             // one CTA per SM
+        h->k1_configured = 1;
     }
-    const int P = max_ctas;
+    const int P = h->k1_ctas;
     PD_REQUIRE(h, P > 0, "pd_rssm_unroll_fwd: kernel does not fit an SM");
     const int Z = a->G * a->C;
     const bool ok = a->T >= 1 && a->BI >= 1 && a->BI <= BROWS && a->BI <= P && a->I >= 1 && a->BI % a->I == 0 &&

@@ -212,11 +212,16 @@ class _AttachGrads(torch.autograd.Function):
 
 class _FusedAdamW:
     """One optimizer of the tuple `init_optimizers` returns (dreamer.py:60-71): torch.optim.AdamW
-    semantics (decoupled weight_decay=0.01, eps, no amsgrad) over one contiguous arena group."""
+    semantics (decoupled weight_decay=0.01, eps, no amsgrad) over one contiguous arena group.
+
+    `state_dict()` / `load_state_dict()` speak torch.optim.AdamW's own layout (per-parameter `state` keyed by the
+    parameter's index in the group, `param_groups[0]['params']` = those indices), so the reference's checkpoint code
+    (tools.py:171-172 save, :195-196 load) round-trips both ways with a `torch.optim.AdamW` over the reference module."""
 
     def __init__(self, owner, gid, lr, eps, betas=(0.9, 0.999), weight_decay=0.01):
         self.owner, self.gid = owner, gid
-        self.defaults = dict(lr=lr, eps=eps, betas=betas, weight_decay=weight_decay)
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                             foreach=None, capturable=False, differentiable=False, fused=None)
         self.param_groups = [dict(params=list(owner._group_params[gid]), **self.defaults)]
         self._alloc()
 
@@ -227,7 +232,9 @@ class _FusedAdamW:
         self.step_t = torch.zeros(1, dtype=torch.int32, device=a.device)
 
     def zero_grad(self, set_to_none=True):
-        # gradients are overwritten (not accumulated) by every training_step; nothing to clear
+        # every training_step overwrites the gradient arena, so there is nothing to clear; the call marks the previous
+        # gradients as consumed (see Dreamer._note_new_grads: accumulation over several backward passes is not supported)
+        self.owner._grads_pending.discard(self.gid)
         return None
 
     @torch.no_grad()
@@ -243,16 +250,51 @@ class _FusedAdamW:
         o.ops.adamw(p, g, self.exp_avg, self.exp_avg_sq, pg["lr"], pg["betas"][0], pg["betas"][1], pg["eps"],
                     pg["weight_decay"], self.step_t)
         o._weights_dirty = True
+        o._grads_pending.discard(self.gid)
+
+    def _slices(self):
+        """(index, offset in the group, numel, shape) of every parameter of the group, in torch's parameter order."""
+        o = self.owner
+        base = o._group_range[self.gid][0]
+        return [(i, o._offsets[id(p)] - base, p.numel(), p.shape) for i, p in enumerate(o._group_params[self.gid])]
 
     def state_dict(self):
-        return dict(state=dict(exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, step=self.step_t),
-                    param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+        step = int(self.step_t.item())
+        state = {}
+        if step > 0:                                          # torch creates the per-parameter state at the first step
+            for i, off, n, shape in self._slices():
+                state[i] = dict(step=torch.tensor(float(step)), exp_avg=self.exp_avg[off:off + n].view(shape).clone(),
+                                exp_avg_sq=self.exp_avg_sq[off:off + n].view(shape).clone())
+        pg = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        pg["params"] = list(range(len(self.owner._group_params[self.gid])))
+        return dict(state=state, param_groups=[pg])
 
     def load_state_dict(self, sd):
         st = sd["state"]
-        self.exp_avg.copy_(st["exp_avg"]); self.exp_avg_sq.copy_(st["exp_avg_sq"]); self.step_t.copy_(st["step"])
+        sl = self._slices()
+        if len(sd["param_groups"]) != 1 or len(sd["param_groups"][0]["params"]) != len(sl):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        ids = list(sd["param_groups"][0]["params"])
+        with torch.no_grad():
+            self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_t.zero_()
+            steps = set()
+            for (i, off, n, shape), key in zip(sl, ids):
+                e = st.get(key)
+                if e is None:
+                    continue
+                if tuple(e["exp_avg"].shape) != tuple(shape):
+                    raise ValueError(f"optimizer state of parameter {i} has shape {tuple(e['exp_avg'].shape)}, expected {tuple(shape)}")
+                self.exp_avg[off:off + n].copy_(e["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(e["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(e["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"parameters of one group carry different step counts {sorted(steps)}: the fused optimizer "
+                                 "keeps one counter per group")
+            if steps:
+                self.step_t.fill_(steps.pop())
         for k, v in sd["param_groups"][0].items():
-            self.param_groups[0][k] = v
+            if k != "params":
+                self.param_groups[0][k] = v
 
 
 # ======================================================================================
@@ -295,6 +337,10 @@ class Dreamer(nn.Module):
         self._ops = None
         self._weights_dirty = True
         self._dp = None           # optional data-parallel reducer (pydreamer_b200.parallel)
+        self._grads_pending = set()
+        # nn.Module.load_state_dict copies into the arena views in place: the tf32 / fp16 shadow arenas and the re-laid
+        # conv weights must be rebuilt before the next kernel reads them
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_weights_dirty", True))
         self._build_registry()
 
     # ------------------------------------------------------------------ arena
@@ -361,19 +407,28 @@ class Dreamer(nn.Module):
         return arena[o:o + p.numel()].view(p.shape)
 
     def _deliver_grads(self, gid, grad_out):
-        """backward() of one of the four losses: scale the group's precomputed gradients by grad_out and
-        make sure `.grad` of its parameters points at them."""
+        """backward() of one of the four losses: scale the group's precomputed gradients by grad_out (a device-side
+        no-op when it is exactly 1, the plain `loss.backward()` of train.py:186-187; a GradScaler under amp or any
+        `(k * loss).backward()` scales them) and make sure `.grad` of its parameters points at them."""
         g = self._group_slice(gid, self._garena)
-        if self._unit_grad_output:
-            pass
-        else:
-            self.ops.rowscale(g.view(1, -1), grad_out.reshape(1).to(g.dtype), 1, 1.0)
+        self.ops.scale_by(g, grad_out.reshape(1).to(device=g.device, dtype=g.dtype))
         for p in self._group_params[gid]:
             if p.grad is None or p.grad.data_ptr() != self._view(self._garena, p).data_ptr():
                 p.grad = self._view(self._garena, p)
 
-    # set False if the caller backwards with a non-unit grad_output (e.g. GradScaler with amp=True)
-    _unit_grad_output = True
+    def _note_new_grads(self):
+        """Every training_step overwrites the gradient arena (it is never accumulated into).  A caller that runs two
+        training steps without an optimizer step / zero_grad in between is accumulating gradients in the reference's
+        semantics; that is not supported here and is said once instead of silently training on the last micro-batch."""
+        if self._grads_pending and not self._warned_accum:
+            import warnings
+            warnings.warn("pydreamer_b200: training_step overwrites the gradients of the previous call (groups "
+                          f"{sorted(self._grads_pending)} were neither stepped nor zero_grad()-ed): gradient accumulation "
+                          "over several training_step calls is not supported")
+            self._warned_accum = True
+        self._grads_pending = set(GROUPS)
+
+    _warned_accum = False
     # forward-only layers (imagination rollout, heads on dreamed features) use fp16 tensor-core operands: the same
     # 10-bit mantissa as TF32 at twice the MMA rate and half the operand traffic; no gradient flows through them.
     fp16_forward = os.environ.get("PD_B200_FP16_FORWARD", "1") != "0"
@@ -395,15 +450,16 @@ class Dreamer(nn.Module):
             self._dp.allreduce_grads(self)
         ws = self._buf("clip", 8)
         self.ops.fill(ws, 0.0)
-        out = {}
+        keys = []
         for i, (gid, key, mx) in enumerate((("wm", "grad_norm", grad_clip), ("probe", "grad_norm_probe", grad_clip),
                                             ("actor", "grad_norm_actor", grad_clip_ac or grad_clip),
                                             ("critic", "grad_norm_critic", grad_clip_ac or grad_clip))):
             g = self._group_slice(gid, self._garena)
             self.ops.sumsq(g, ws[i:i + 1])
             self.ops.clip_scale(g, ws[i:i + 1], mx, ws[4 + i:5 + i])
-            out[key] = ws[4 + i]
-        return out
+            keys.append(key)
+        norms = ws[4:8].clone()                 # the caller's own copy (the workspace is rewritten by the next call)
+        return {k: norms[i] for i, k in enumerate(keys)}
 
     def init_state(self, batch_size):
         dev = next(self.parameters()).device
@@ -595,11 +651,13 @@ class Dreamer(nn.Module):
         want_grad = torch.is_grad_enabled()
         with torch.no_grad():
             if want_grad:
+                self._note_new_grads()
                 self._sync_target_critic()
             flags = (bool(do_open_loop), bool(do_image_pred), bool(do_dream_tensors and self.wm.decoder.image is not None))
             if flags[0] and want_grad:
                 raise NotImplementedError("do_open_loop is the evaluation branch (train.py:353-359 runs it under no_grad)")
-            if self.use_cuda_graph and noise is None and want_grad and self._arena.is_cuda and not any(flags):
+            graphed = self.use_cuda_graph and noise is None and want_grad and self._arena.is_cuda and not any(flags)
+            if graphed:
                 wm_out, ac_out = self._graphed_core(obs, in_state, T, B, I, H)
             else:                                   # logging / evaluation steps (~10 % of steps) are launched eagerly
                 wm_out, ac_out = self._core(obs, in_state, T, B, I, H, noise, want_grad, flags=flags)
@@ -612,8 +670,17 @@ class Dreamer(nn.Module):
             loss_actor = _AttachGrads.apply(loss_actor, self, "actor", *gp["actor"])
             loss_critic = _AttachGrads.apply(loss_critic, self, "critic", *gp["critic"])
         metrics = dict(wm_out["metrics"]); metrics.update(ac_out["metrics"])
+        # the step's scalars live in reused workspace / CUDA-graph buffers: hand the caller its own copy (one small gather
+        # kernel), so metrics kept across steps (train.py:204-214 accumulates them for logging) stay what they were
+        keys = list(metrics)
+        snap = torch.stack([metrics[k].detach().reshape(()).to(torch.float32) for k in keys])
+        metrics = {k: snap[i] for i, k in enumerate(keys)}
         tensors = dict(wm_out["tensors"])
         tensors.update(policy_value=ac_out["value"][0].reshape(T, B, I).mean(-1))
+        if not graphed:
+            # logging / evaluation steps (the ones whose tensors train.py actually reads) return private copies; on the
+            # CUDA-graph steady-state path `tensors` stay views of the step workspace, valid until the next call
+            tensors = {k: v.clone() for k, v in tensors.items()}
         return (loss_model, loss_probe, loss_actor, loss_critic), wm_out["out_state"], metrics, tensors, \
             ac_out.get("dream_tensors", {})
 

@@ -1,7 +1,8 @@
 """Data-parallel learner step: the inner loop of the reference's train.py (146-303) around the drop-in Dreamer, without
 mlflow.  SURVEY.md §8(f) row N1.
 
-  * one process per GPU; each rank feeds its own replay shard; gradients are all-reduced once per step (parallel.py)
+  * one process per GPU; each rank feeds its own replay shard (its own batch iterator: nothing here draws random
+    numbers, so shards differ exactly as the caller's iterators do); gradients are all-reduced once per step (parallel.py)
   * truncated BPTT state carry per data stream (`states[wid]`, train.py:168-178, `keep_state`)
   * checkpoints in the reference's format (tools.py:164-174: {'epoch', 'model_state_dict', 'optimizer_{i}_state_dict'}), so the
     unmodified CPU generators (generator.py:105-116) keep loading `latest.pt` into the reference `Dreamer`.
@@ -48,19 +49,16 @@ class Learner:
         metrics.update(grad_metrics)
         return metrics, tensors, dream
 
-    def train_on_episodes(self, directory, num_steps, skip_first=True):
-        """Gradient steps straight from a directory of the reference's episode `.npz` files (episodes.py): raw uint8 /
-        integer batches cross PCIe and are converted on the device (preprocess.py).  train.py:104-131,146-166 without
-        the DataLoader workers.  Returns the metrics of the last step."""
-        from .episodes import EpisodeDirectory, SequentialBatches
+    def train_on_batches(self, batches, num_steps):
+        """Gradient steps from an iterator of RAW replay batches — what the reference's own `DataSequential`
+        (pydreamer/data.py:127-305, which stays the caller's: the replay pipeline is outside this package) yields before
+        its `Preprocessor`: uint8 HWC images, integer actions, (T,B,...) arrays.  They cross PCIe in that format and are
+        converted on the device (preprocess.py; train.py:104-131,146-166 without the DataLoader workers).  In a
+        data-parallel job every rank passes its OWN iterator (own replay shard / own numpy seed).  Returns the metrics of
+        the last step."""
         from .preprocess import GpuPreprocessor
 
-        conf = self.conf
-        batches = SequentialBatches(EpisodeDirectory(directory), conf.batch_length, conf.batch_size, skip_first=skip_first,
-                                    reset_interval=getattr(conf, "reset_interval", 0),
-                                    buffer_size=getattr(conf, "buffer_size", 0),
-                                    allow_mid_reset=getattr(conf, "allow_mid_reset", False))
-        pre = GpuPreprocessor(conf, self.device)
+        pre = GpuPreprocessor(self.conf, self.device)
         keys = ("image", "action", "reward", "terminal", "reset")
         metrics = None
         for _, raw in zip(range(num_steps), batches):
@@ -76,12 +74,16 @@ class Learner:
         torch.save(ck, path)
 
     def load_checkpoint(self, path, map_location=None):
+        """tools.py:177-197.  The optimizer entries are torch.optim.AdamW state dicts (what the reference's loop writes and
+        what `_FusedAdamW.state_dict` emits), so Adam moments and step counts resume whichever side wrote the file."""
         ck = torch.load(path, map_location=map_location or self.device)
         self.model.load_state_dict(ck["model_state_dict"])
-        self.model._weights_dirty = True
         for i, opt in enumerate(self.optimizers):
             key = f"optimizer_{i}_state_dict"
-            if key in ck and "state" in ck[key] and "exp_avg" in ck[key]["state"]:          # our own optimizer format
+            if key in ck:
                 opt.load_state_dict(ck[key])
+            else:
+                import warnings
+                warnings.warn(f"checkpoint {path} has no {key}: optimizer {i} restarts from zero moments")
         self.steps = ck["epoch"]
         return self.steps

@@ -56,6 +56,7 @@ class NativeOps:
         if rc != 0:
             raise RuntimeError(f"pd_create failed ({rc}): device {idx} is not an sm_100 GPU or the driver is too old")
         self.h = h
+        self._index = int(idx)
         self.gemm_profile = None   # list of (start_event, end_event, flops) when bench.py profiles a step
 
     def __del__(self):
@@ -67,6 +68,10 @@ class NativeOps:
 
     # ------------------------------------------------------------------ plumbing
     def _s(self):
+        # kernels launch on the CURRENT device: refuse to enqueue this handle's work on another GPU's context
+        if torch.cuda.current_device() != self._index:
+            raise RuntimeError(f"pydreamer_b200: current CUDA device is {torch.cuda.current_device()} but this model lives on "
+                               f"cuda:{self._index}; wrap the call in `with torch.cuda.device({self._index})`")
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ck(self, rc, name):
@@ -265,6 +270,11 @@ class NativeOps:
         M, N = x.shape
         self._ck(self.lib.pd_rowscale(self.h, M, N, _ptr(x), _ld(x), _ptr(scale), int(scale_div), float(alpha),
                                       self._s()), "pd_rowscale")
+
+    def scale_by(self, x, scale=None, alpha=1.0):
+        """x *= alpha * scale[0] (no operand rounding; a factor of exactly 1 is a no-op on the device)."""
+        assert x.is_contiguous()
+        self._ck(self.lib.pd_scale_by(self.h, _ptr(x), x.numel(), _ptr(scale), float(alpha), self._s()), "pd_scale_by")
 
     def group_sum(self, x, I, out):
         R, W = out.shape

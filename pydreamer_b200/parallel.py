@@ -24,6 +24,4 @@ class GradAllReduce:
     def allreduce_grads(self, model):
         g = model._garena
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-        if self._scale is None or self._scale.device != g.device:
-            self._scale = torch.full((1,), 1.0 / self.world, dtype=g.dtype, device=g.device)
-        model.ops.rowscale(g.view(1, -1), self._scale, 1, 1.0)
+        model.ops.scale_by(g, None, 1.0 / self.world)        # exact fp32 scaling (no operand rounding)

@@ -58,23 +58,26 @@ def test_learner_steps_carry_state_and_checkpoint_roundtrip(ref_ops, tmp_path):
             break
 
 
-def test_learner_trains_from_episode_files(ref_ops, tmp_path):
-    """Episode .npz files (reference replay format) -> SequentialBatches -> device-side preprocessing -> gradient steps."""
+def test_learner_trains_from_raw_replay_batches(ref_ops):
+    """Raw replay batches (uint8 HWC images, integer actions: what the reference's DataSequential yields) -> device-side
+    preprocessing -> gradient steps, state carried across consecutive windows."""
     import numpy as np
-
-    from pydreamer_b200.episodes import EpisodeDirectory, save_episode
 
     conf = make_conf("tiny", device="cpu", reset_interval=0)
     rng = np.random.default_rng(0)
-    for ep in range(2):
-        n = 30 + 7 * ep
-        data = dict(image=rng.integers(0, 256, (n, 64, 64, 3), dtype=np.uint8), action=rng.integers(0, conf.action_dim, n),
-                    reward=rng.normal(size=n).astype(np.float32), terminal=np.zeros(n, bool), reset=np.zeros(n, bool))
-        data["reset"][0] = True
-        save_episode(data, tmp_path, ep, ep)
-    assert EpisodeDirectory(tmp_path).count_steps() == (2, 65, 2)
-    np.random.seed(3)
+    T, B = conf.batch_length, conf.batch_size
+
+    def batches():
+        first = True
+        while True:
+            reset = np.zeros((T, B), bool)
+            reset[0] = first
+            first = False
+            yield dict(image=rng.integers(0, 256, (T, B, 64, 64, 3), dtype=np.uint8),
+                       action=rng.integers(0, conf.action_dim, (T, B)), reward=rng.normal(size=(T, B)).astype(np.float32),
+                       terminal=np.zeros((T, B), bool), reset=reset)
+
     lr = Learner(conf, "cpu")
-    metrics = lr.train_on_episodes(tmp_path, 3)
+    metrics = lr.train_on_batches(batches(), 3)
     assert lr.steps == 3 and torch.isfinite(metrics["loss_model"]) and float(metrics["grad_norm"]) > 0
     assert lr.states[0][0].shape == (conf.batch_size, conf.deter_dim)          # state carried across the windows
