@@ -11,9 +11,17 @@ the reference's own `train/fps` (train.py:243-246) minus data loading.  Prints O
   value : steps/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the public module API with the batch copied from pinned host memory every step and
           the four losses read back to the host inside the timed region
-  roofline : the dominant kernel (pd_gemm_tf32_kernel: tcgen05 TF32 GEMM) — algorithmic FLOPs of every launch in
-          one step / their CUDA-event durations, against MEASURED_PEAKS.json
-  cpu_baseline : the reference implementation on this box's host cores (rank 0, N=1), bounded sample
+  roofline : the dominant kernel (pd_gemm_tf32[_2cta]_kernel: tcgen05 GEMM, kind::tf32 and kind::f16 launches) — algorithmic
+          FLOPs of every launch in one step / their CUDA-event durations, against MEASURED_PEAKS.json; split per operand
+          kind, plus the top HBM-bound kernels (algorithmic bytes / CUDA-event time vs the measured copy bandwidth);
+          `traffic` = DRAM bytes of the largest GEMM launch read from the committed ncu summary (profiles/)
+  cpu_baseline : the unmodified reference on this box's host cores at the FULL batch (rank 0, N=1): 1 small warm-up +
+          2 timed steps
+  reference_gpu_eager : the unmodified reference (eager PyTorch fp32, cudnn.benchmark, train.py:30-31,143,166) on the same
+          GPU, CUDA events, its own clock record — the denominator of north_star's 20x target (rank 0, N=1)
+
+`--impl reference` times the reference's CPU path at the full batch; a CPU step takes ~15 s, so it times
+min(K, 3) steps after min(W, 1) warm-up and reports THOSE counts in `steps` / `warmup`.
 """
 import argparse
 import json
@@ -42,6 +50,7 @@ def parse():
     ap.add_argument("--config", default="atari")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-eager-on-this-GPU measurement")
     ap.add_argument("--ref-device", default="cpu", help="device of the --impl reference arm (cpu per the contract)")
     ap.add_argument("--ref-batch", type=int, default=0, help="sequences per reference sample step (0 = auto)")
     ap.add_argument("--dump-gemm-profile", default="", help="write the per-shape GEMM timing table of one step here")
@@ -63,6 +72,20 @@ def peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def ncu_summary():
+    """profiles/ncu_summary.json: per-kernel numbers read from the committed `ncu --set full` captures (DRAM bytes, tensor
+    pipe, duration) by tools/ncu_summarize.py.  bench.py only quotes it (a number taken under a profiler is never a bench
+    value); absent -> {}."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f)
+        except Exception:
+            pass
+    return {}
 
 
 class ClockSampler:
@@ -162,24 +185,23 @@ def pick_cpu_threads(conf, requested=0):
 
 
 def time_reference(conf, device, B, steps, warmup):
-    """Seconds per gradient step of the reference path at batch B (its own Dreamer if installed, else the oracle)."""
+    """Seconds per gradient step of the reference path at batch B (its own Dreamer if installed, else the oracle).
+    CPU: wall clock per step.  GPU: CUDA events around the timed steps (eager launches are asynchronous)."""
     from pydreamer_b200.replay import synthetic_batch
 
     torch.distributions.Distribution.set_default_validate_args(False)       # train.py:30
     RefDreamer, kind = reference_module()
     obs = synthetic_batch(conf, seed=1234, B=B, device=device)
-    times = []
+    on_gpu = str(device) != "cpu"
     if kind == "reference":
-        if str(device) != "cpu":
+        if on_gpu:
             torch.backends.cudnn.benchmark = True                            # train.py:31
         model = RefDreamer(conf).to(device)
         opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
-        state = model.init_state(B * conf.iwae_samples)
-        for it in range(warmup + steps):
-            if str(device) != "cpu":
-                torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            losses, state, *_ = model.training_step(obs, state)
+        st = {"s": model.init_state(B * conf.iwae_samples)}
+
+        def one():
+            losses, st["s"], *_ = model.training_step(obs, st["s"])
             for o in opts:
                 o.zero_grad()
             for l in losses:
@@ -187,10 +209,6 @@ def time_reference(conf, device, B, steps, warmup):
             model.grad_clip(conf.grad_clip, conf.grad_clip_ac)
             for o in opts:
                 o.step()
-            if str(device) != "cpu":
-                torch.cuda.synchronize()
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
     else:
         from oracle import dreamer_oracle as O
         from pydreamer_b200.dreamer import Dreamer
@@ -199,22 +217,46 @@ def time_reference(conf, device, B, steps, warmup):
               for k, v in Dreamer(conf).state_dict().items()}
         params = [v for v in sd.values() if v.requires_grad]
         opt = torch.optim.AdamW(params, lr=conf.adam_lr, eps=conf.adam_eps)
-        state = (torch.zeros(B, conf.deter_dim, device=device), torch.zeros(B, conf.stoch_dim * conf.stoch_discrete, device=device))
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
+        st = {"s": (torch.zeros(B, conf.deter_dim, device=device),
+                    torch.zeros(B, conf.stoch_dim * conf.stoch_discrete, device=device))}
+
+        def one():
             noise = O.draw_noise(conf, conf.batch_length, B, device=device)
-            res = O.training_step(sd, conf, obs, state, noise)
+            res = O.training_step(sd, conf, obs, st["s"], noise)
             opt.zero_grad()
             for l in res["losses"]:
                 l.backward()
             torch.nn.utils.clip_grad_norm_(params, conf.grad_clip)
             opt.step()
-            state = res["out_state"]
-            if str(device) != "cpu":
-                torch.cuda.synchronize()
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), kind
+            st["s"] = res["out_state"]
+
+    for _ in range(warmup):
+        one()
+    if on_gpu:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1000.0 / steps, kind
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    return (time.perf_counter() - t0) / steps, kind
+
+
+def time_reference_cpu_full(conf, threads_requested=0, steps=2):
+    """The reference's CPU path at the FULL benchmark batch: thread-count calibration on 1-sequence steps, one 5-sequence
+    warm-up (allocator / oneDNN primitive caches), then `steps` timed full-batch steps.  -> (s/step, kind, cores, sample)"""
+    cores = pick_cpu_threads(conf, threads_requested)
+    time_reference(conf, "cpu", max(1, conf.batch_size // 10), 1, 0)
+    sec, kind = time_reference(conf, "cpu", conf.batch_size, steps, 0)
+    sample = (f"full batch: {conf.batch_size} sequences x T={conf.batch_length}, H={conf.imag_horizon}, I={conf.iwae_samples}; "
+              f"1 warm-up step at {max(1, conf.batch_size // 10)} sequences + {steps} timed full-batch steps ({sec:.1f} s each) "
+              f"on {cores} threads")
+    return sec, kind, cores, sample
 
 
 def run_reference(args):
@@ -222,27 +264,41 @@ def run_reference(args):
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return                               # rank 0 alone times the CPU reference; the others exit without touching CUDA
     conf = make_conf(args.config, device=args.ref_device)
-    cores = pick_cpu_threads(conf, args.cpu_threads) if args.ref_device == "cpu" else 0
     full_B = conf.batch_size
-    B = args.ref_batch or (max(1, full_B // 10) if args.ref_device == "cpu" else full_B)
-    sec, kind = time_reference(conf, args.ref_device, B, args.steps, args.warmup)
-    scale = full_B / B                      # the CPU path is throughput-bound: time is linear in sequences per batch
-    sps = 1.0 / (sec * scale)
     T, I, H = conf.batch_length, conf.iwae_samples, conf.imag_horizon
-    sample = (f"{B} of {full_B} sequences x T={T}, H={H} per sample step on {args.ref_device}; "
-              f"steps/s = 1 / (sample seconds x {scale:g})")
+    if args.ref_device == "cpu":
+        # a full-batch CPU step is ~15 s: time min(K,3) of them after min(W,1) warm-up and SAY so in steps / warmup
+        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        cores = pick_cpu_threads(conf, args.cpu_threads)
+        B = args.ref_batch or full_B
+        if warmup:
+            time_reference(conf, "cpu", max(1, B // 10), 1, 0)
+        sec, kind = time_reference(conf, "cpu", B, steps, 0)
+        clocks = None
+        sample = (f"{B} of {full_B} sequences x T={T}, H={H} per step on cpu, {cores} threads; {steps} timed steps after "
+                  f"{warmup} warm-up step (at {max(1, B // 10)} sequences); requested --steps {args.steps} --warmup {args.warmup}")
+    else:
+        steps, warmup, cores, B = args.steps, max(args.warmup, 3), 0, args.ref_batch or full_B
+        with ClockSampler(0) as cs:
+            sec, kind = time_reference(conf, args.ref_device, B, steps, warmup)
+        clocks = cs.summary()
+        sample = f"{B} of {full_B} sequences x T={T}, H={H} per step on {args.ref_device} (eager PyTorch fp32, cudnn.benchmark)"
+    scale = full_B / B                      # 1 unless --ref-batch asks for a sub-batch
+    sps = 1.0 / (sec * scale)
     line = dict(metric="grad_steps_per_sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 * sec * scale, higher_is_better=True,
+                steps=steps, warmup=warmup, ms_per_step=1000.0 * sec * scale, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 imagined_samples_per_sec=sps * T * full_B * I * H,
-                config=dict(workload=f"{args.config}: Dreamer.training_step+backward+clip+AdamW, B={full_B} T={T} H={H} "
-                                     f"deter={conf.deter_dim} stoch={conf.stoch_dim}x{conf.stoch_discrete}",
-                            global_batch=full_B, seq_len=T),
-                cpu_baseline=dict(value=sps, unit="steps/s", cores=cores if args.ref_device == "cpu" else 0, kind=kind,
-                                  sample=sample),
+                config=dict(workload=f"{args.config}: Dreamer.training_step+4x backward+grad_clip+4x AdamW, per-GPU B={full_B} "
+                                     f"T={T} H={H} I={I} deter={conf.deter_dim} stoch={conf.stoch_dim}x{conf.stoch_discrete} "
+                                     f"image 64x64x3", global_batch=full_B, seq_len=T, parallelism="cpu" if cores else "1 gpu eager",
+                            ref_device=args.ref_device),
+                cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    if clocks is not None:
+        line["clocks"] = clocks
     print(json.dumps(line))
 
 
@@ -260,7 +316,13 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a stuck collective aborts the job after 3 minutes instead of wedging the box (NCCL watchdog), and so does the
+        # Python-level watchdog below if the device itself stops answering
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        if args.watchdog <= 0:
+            import faulthandler
+            faulthandler.dump_traceback_later(900, exit=True)
     conf = make_conf(args.config, device=str(dev))
     T, B, I, H = conf.batch_length, conf.batch_size, conf.iwae_samples, conf.imag_horizon
     model = Dreamer(conf).to(dev)
@@ -309,12 +371,18 @@ def run_ours(args):
 
     n0 = model.ops.launch_count()
     step(dev_obs)                                    # first call of a shape is always launched kernel by kernel
-    launches = model.ops.launch_count() - n0         # kernels per step (a CUDA-graph replay re-issues the same ones)
+    launches = model.ops.launch_count() - n0         # this library's kernels in one eagerly launched step
     for _ in range(max(args.warmup, 3) - 1):
         step(dev_obs)
+    n1 = model.ops.launch_count()
     with ClockSampler(local) as cs:
         ms = timed(lambda: step(dev_obs), args.steps)
     clocks = cs.summary()
+    # kernels of this library that ran in the timed region: the ones launched from Python (gradient hand-over, clip, AdamW)
+    # plus, per replay, the kernel nodes the step's CUDA graph re-issues (counted when it was captured)
+    eager_in_region = model.ops.launch_count() - n1
+    graph_nodes = max([g.get("kernels", 0) for g in model._graphs.values() if g.get("graph") is not None] or [0])
+    launches_timed = eager_in_region + graph_nodes * args.steps
 
     # End to end through the public API: every step's batch travels from pinned host memory to the device inside the
     # timed region and its four losses travel back.  Like any input pipeline (the reference uses DataLoader workers +
@@ -397,8 +465,35 @@ def run_ours(args):
     step(dev_obs)                                                      # warm-up of this schedule (allocates its scratch buffers)
     torch.cuda.synchronize()
     model.ops.gemm_profile = []
+    # the HBM-bound kernels with the most traffic: CUDA events around each launch + their ALGORITHMIC bytes (every operand
+    # read once, every result written once)
+    hbm_prof = {}
+
+    def timed_op(name, nbytes):
+        orig = getattr(model.ops, name)
+
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig(*a, **k); e1.record()
+            hbm_prof.setdefault(name, []).append((e0, e1, nbytes(*a, **k)))
+            return r
+        setattr(model.ops, name, wrapper)
+        return lambda: delattr(model.ops, name)
+
+    nb = lambda *ts: float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+    undo = [
+        # (col, NB, Hin, Win, Cc, k, bias, target, tgt_div, dec, diff, loss, csum)
+        timed_op("col2im_imgloss", lambda col, NB, Hin, Win, Cc, k, bias, target, div, dec, diff, loss, csum:
+                 nb(col, dec, diff) + nb(target) / max(1, conf.iwae_samples)),
+        timed_op("ln_elu_fwd", lambda x, g, b_, eps, y, mean, rstd, y16=None: nb(x, y, y16)),
+        timed_op("adamw", lambda p_, g, m, v, *a: 7.0 * nb(p_)),       # read p,g,m,v + write p,m,v
+        timed_op("col2im", lambda col, Hin, Win, k, bias, act, out, round_out=True: nb(col, out)),
+        timed_op("im2col", lambda inp, k, korder, col, round_out=True: nb(col) + float(inp.numel() * 4)),
+    ]
     step(dev_obs)
     torch.cuda.synchronize()
+    for u in undo:
+        u()
     prof, model.ops.gemm_profile = model.ops.gemm_profile, None
 
     class PhaseTimer:
@@ -428,10 +523,31 @@ def run_ours(args):
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     pk = peaks()
+    # per operand kind: kind::f16 launches (pd_gemm_f16) carry "f16" in their shape key, everything else runs kind::tf32
+    buckets = {}
+    for e0, e1, f, shp in prof:
+        kind = "f16" if shp[3] == "f16" else "tf32"
+        bk = buckets.setdefault(kind, dict(launches=0, ms=0.0, flops=0.0))
+        bk["launches"] += 1; bk["ms"] += e0.elapsed_time(e1); bk["flops"] += f
+    for kind, bk in buckets.items():
+        bk["tflops"] = bk["flops"] / max(bk["ms"], 1e-9) / 1e9
+        # measured denominator: cuBLAS bf16 sustained (16-bit operands); TF32's MMA rate is half of the 16-bit rate
+        bk["peak"] = pk["bf16_sustained"] * (1.0 if kind == "f16" else 0.5)
+        bk["frac"] = bk["tflops"] / bk["peak"]
+        bk["share_of_gemm_flops"] = bk["flops"] / max(gemm_flops, 1.0)
+    hbm_kernels = []
+    for name, rows in hbm_prof.items():
+        ms_k = sum(a.elapsed_time(b) for a, b, _ in rows)
+        by = sum(c for _, _, c in rows)
+        hbm_kernels.append(dict(kernel=name, launches=len(rows), ms=round(ms_k, 4), algorithmic_bytes=by,
+                                achieved_gbs=by / max(ms_k, 1e-9) / 1e6, frac=by / max(ms_k, 1e-9) / 1e6 / pk["hbm_gbs"]))
+    hbm_kernels.sort(key=lambda r: -r["ms"])
+    ncu = ncu_summary()
     steps_per_s = world * args.steps / (ms / 1000.0)
     e2e_per_s = world * args.steps / (ms_e2e / 1000.0)
     per_step_samples = T * B * I * H
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    top = ncu.get("dominant_gemm_launch", {})
     line = dict(
         metric="grad_steps_per_sec", value=steps_per_s, unit="steps/s", n_gpus=world, steps=args.steps,
         global_steps_per_sec=steps_per_s / world,
@@ -441,34 +557,49 @@ def run_ours(args):
         config=dict(workload=f"{args.config}: Dreamer.training_step+4x backward+grad_clip+4x AdamW, per-GPU B={B} T={T} H={H} "
                              f"I={I} deter={conf.deter_dim} stoch={conf.stoch_dim}x{conf.stoch_discrete} image 64x64x3",
                     global_batch=B * world, seq_len=T, parallelism=f"dp{world}",
-                    l2="per-step working set (~15 GB of activations) is far larger than the 126 MB L2; no flush needed"),
+                    l2="per-step working set (GBs of activations) is far larger than the 126 MB L2; no flush needed"),
         e2e=dict(value=e2e_per_s, unit="steps/s", h2d_bytes_per_step=obs_bytes(host), d2h_bytes_per_step=16,
                  ms_per_step=ms_e2e / args.steps),
         e2e_uint8=e2e_u8,
-        gpu_launches=int(launches) * args.steps,
+        gpu_launches=int(launches_timed),
+        gpu_launches_note=f"{graph_nodes} kernel nodes per CUDA-graph replay x {args.steps} steps + {eager_in_region} launched from "
+                          f"Python in the timed region (gradient hand-over, clip, AdamW); one eagerly launched step = {int(launches)}",
         phases_ms_eager=phases,
         launches_per_step=int(launches),
         clocks=clocks,
-        roofline=dict(bound="tensor", kernel="pd_gemm_tf32_kernel (tcgen05.mma kind::tf32)", achieved=achieved,
-                      peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"],
-                      peak_source=pk["source"] + ": cuBLAS bf16 sustained; tf32 nominal peak is half of bf16",
-                      traffic=171.3e6 if args.config == "atari" else None,
-                      traffic_note="dram read+write of the largest TF32 launch (2500x6144x2048, 2-CTA kernel) from "
-                                   "profiles/r01_c_gemm_2cta_2500x6144x2048_full.ncu-rep; its algorithmic bytes are 132 MB",
+        roofline=dict(bound="tensor", kernel="pd_gemm_tf32_kernel / pd_gemm_tf32_2cta_kernel (tcgen05.mma, kind::tf32 and kind::f16 launches)",
+                      achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"],
+                      peak_source=pk["source"] + ": cuBLAS bf16 sustained; kind::tf32 launches can reach half of it",
+                      traffic=top.get("dram_bytes"), traffic_note=top.get("note"),
+                      by_operand_kind=buckets,
                       gemm_launches_per_step=len(prof), gemm_ms_per_step=gemm_ms,
                       gemm_share_of_step=gemm_ms / (ms / args.steps), gemm_flops_per_step=gemm_flops,
                       step_algorithmic_tflop=ALGO_FLOPS_ATARI / 1e12 if args.config == "atari" else None,
-                      step_tflops=(ALGO_FLOPS_ATARI / 1e12) / (ms / args.steps / 1000.0) if args.config == "atari" else None),
+                      step_tflops=(ALGO_FLOPS_ATARI / 1e12) / (ms / args.steps / 1000.0) if args.config == "atari" else None,
+                      hbm_kernels=hbm_kernels[:5], hbm_peak_gbs=pk["hbm_gbs"],
+                      ncu_summary=ncu.get("kernels")),
     )
+    if rank == 0 and world == 1 and not args.no_ref_gpu:
+        # the denominator of north_star's ">= 20x the reference's 1-GPU PyTorch steps/s": the unmodified reference, eager fp32
+        # on this same GPU (train.py:30-31,143,166), after our own measurement so nothing of it overlaps ours
+        try:
+            model._ws.clear(); model._graphs.clear()
+            torch.cuda.empty_cache()
+            gconf = make_conf(args.config, device=str(dev))
+            with ClockSampler(local) as cs2:
+                sec_g, kind_g = time_reference(gconf, str(dev), B, 20, 5)
+            if kind_g == "reference":
+                line["reference_gpu_eager"] = dict(value=1.0 / sec_g, unit="steps/s", ms_per_step=1000.0 * sec_g, steps=20,
+                                                   warmup=5, clocks=cs2.summary(),
+                                                   how="unmodified reference Dreamer on the same GPU: eager PyTorch fp32, "
+                                                       "cudnn.benchmark, TF32 matmul off (torch default), CUDA events")
+                line["vs_reference_gpu_eager"] = dict(ratio=steps_per_s * sec_g, e2e_ratio=e2e_per_s * sec_g, target=20.0)
+        except Exception as e:                   # the reference arm must never take the headline down with it
+            line["reference_gpu_eager"] = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cconf = make_conf(args.config, device="cpu")
-        cores = pick_cpu_threads(cconf, args.cpu_threads)
-        Bs = max(1, B // 10)
-        sec, kind = time_reference(cconf, "cpu", Bs, 1, 1)
-        scale = B / Bs
-        line["cpu_baseline"] = dict(value=1.0 / (sec * scale), unit="steps/s", cores=cores, kind=kind,
-                                    sample=f"{Bs} of {B} sequences x T={T}, H={H}: 1 warm-up + 1 timed sample step "
-                                           f"({sec:.1f} s); steps/s = 1/(sample s x {scale:g})")
+        sec, kind, cores, sample = time_reference_cpu_full(cconf, args.cpu_threads, steps=2)
+        line["cpu_baseline"] = dict(value=1.0 / sec, unit="steps/s", cores=cores, kind=kind, sample=sample)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

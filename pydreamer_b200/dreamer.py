@@ -821,8 +821,10 @@ class Dreamer(nn.Module):
             torch.cuda.synchronize()
             try:
                 g = torch.cuda.CUDAGraph()
+                k0 = self.ops.launch_count()
                 with torch.cuda.graph(g):
                     st["out"] = self._core(st["obs"], st["state"], T, B, I, H, None, True, force_weights=True)
+                st["kernels"] = self.ops.launch_count() - k0      # kernel nodes of this library in the graph
                 st["graph"] = g
             except Exception as e:                           # keep running eagerly (same kernels), say so once
                 st["failed"] = True
