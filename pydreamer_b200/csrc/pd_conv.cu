@@ -173,7 +173,11 @@ __global__ void col2im_kernel(long total, int Hin, int Win, int Hout, int Wout, 
     }
 }
 
-// One block per decoded image: NCHW traversal (x fastest) for coalesced dec/target/diff access.
+// One block per decoded image: NCHW traversal (x fastest) for coalesced dec/target/diff access.  A thread folds ALL
+// channels of its output pixel in one pass over the (pixel, tap) pieces of the column matrix (Cc <= 4: the decoder's
+// last layer has 1 or 3), so every 32-byte sector of `col` is fetched once instead of once per channel
+// (r02 ncu: 3.15 GB of DRAM reads for a 0.97 GB column matrix with the channel-outer loop).
+template <int CMAX>
 __global__ void __launch_bounds__(256)
 col2im_imgloss_kernel(int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* __restrict__ col, long ldcol,
                       const float* __restrict__ bias, const float* __restrict__ target, int tgt_div,
@@ -185,20 +189,45 @@ col2im_imgloss_kernel(int Hin, int Win, int Hout, int Wout, int Cc, int k, const
     const int per = Cc * plane;
     const float* tg = target + (n / tgt_div) * (long)per;
     float acc = 0.f;
-    for (int c = 0; c < Cc; ++c) {
-        float cacc = 0.f;
-        for (int i = threadIdx.x; i < plane; i += blockDim.x) {
-            int x = i % Wout;
-            int y = i / Wout;
-            float v = col2im_gather(col, ldcol, n, y, x, c, Hin, Win, Cc, k) + bias[c];
-            float d = v - tg[c * plane + i];
-            dec[n * per + c * plane + i] = v;
-            diff[n * per + c * plane + i] = d;
-            acc += d * d;
-            cacc += d;
+    float cacc[CMAX], bv[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) { cacc[c] = 0.f; bv[c] = c < Cc ? bias[c] : 0.f; }
+    for (int i = threadIdx.x; i < plane; i += blockDim.x) {
+        const int x = i % Wout;
+        const int y = i / Wout;
+        float v[CMAX];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) v[c] = 0.f;
+        for (int kh = y & 1; kh < k; kh += 2) {                 // same tap order as col2im_gather (bit-identical sums)
+            const int iy = (y - kh) >> 1;
+            if (iy < 0) break;
+            if (iy >= Hin) continue;
+            for (int kw = x & 1; kw < k; kw += 2) {
+                const int ix = (x - kw) >> 1;
+                if (ix < 0) break;
+                if (ix >= Win) continue;
+                const float* p = col + ((n * Hin + iy) * Win + ix) * ldcol + (long)(kh * k + kw) * Cc;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c)
+                    if (c < Cc) v[c] += p[c];
+            }
         }
-        float cs = pd_block_sum(cacc, sh);
-        if (threadIdx.x == 0) csum[n * Cc + c] = cs;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < Cc) {
+                const float o = v[c] + bv[c];
+                const float d = o - tg[c * plane + i];
+                dec[n * per + c * plane + i] = o;
+                diff[n * per + c * plane + i] = d;
+                acc += d * d;
+                cacc[c] += d;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const float cs = pd_block_sum(cacc[c], sh);             // uniform trip count: every thread takes part
+        if (c < Cc && threadIdx.x == 0) csum[n * Cc + c] = cs;
     }
     float s = pd_block_sum(acc, sh);
     if (threadIdx.x == 0) loss[n] = 0.5f * s;
@@ -311,8 +340,9 @@ int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, con
                       const float* bias, const float* target, int tgt_div, float* dec, float* diff, float* loss,
                       float* csum, void* stream) {
     int Hout = (Hin - 1) * 2 + k, Wout = (Win - 1) * 2 + k;
-    col2im_imgloss_kernel<<<NB, 256, 0, (cudaStream_t)stream>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target,
-                                                                tgt_div > 0 ? tgt_div : 1, dec, diff, loss, csum);
+    PD_REQUIRE(h, Cc >= 1 && Cc <= 4, "pd_col2im_imgloss: %d image channels (1..4 supported)", Cc);
+    col2im_imgloss_kernel<4><<<NB, 256, 0, (cudaStream_t)stream>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target,
+                                                                   tgt_div > 0 ? tgt_div : 1, dec, diff, loss, csum);
     PD_CHECK_LAUNCH(h, "col2im_imgloss");
     return PD_OK;
 }

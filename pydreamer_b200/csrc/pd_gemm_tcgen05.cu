@@ -730,6 +730,29 @@ int make_im2col_map(pd_handle* h, CUtensorMap* tm, const float* base, int NB, in
     return PD_OK;
 }
 
+// Split-K factor for an accumulating GEMM (weight gradients: few output tiles, K = rows of the batch): the factor that
+// minimises waves x (k-blocks per unit + per-unit epilogue), waves = ceil(tiles * splits / slots).  Filling the chip once
+// (splits = slots / tiles) is not the same thing: 96 tiles on 148 SMs leave a third of the chip idle unsplit, 3 splits
+// give 288 units = 1.95 waves of a third of the work each.
+int pick_splits(int tiles, int kb_total, int slots, int min_kb) {
+    int maxs = kb_total / min_kb;
+    if (maxs < 1) maxs = 1;
+    if (maxs > 4 * slots) maxs = 4 * slots;
+    const double epi_kb = 6.0;                 // a unit's TMEM drain + TMA reduce-add, in k-block times
+    int best = 1;
+    double best_cost = 1e300;
+    for (int sp = 1; sp <= maxs; ++sp) {
+        const int kbs = pd_cdiv(kb_total, sp);
+        const int eff = pd_cdiv(kb_total, kbs);               // units really created (no empty ones)
+        if (eff != sp) continue;
+        const long units = (long)tiles * eff;
+        const long waves = (units + slots - 1) / slots;
+        const double cost = (double)waves * ((double)kbs + epi_kb);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+    }
+    return best;
+}
+
 }  // namespace
 
 // Implicit-GEMM convolution launcher.  mode 1: C[pixels, N] = im2col(X) * B   (B: [N][K] or, b_mn, [K][N]; K = (tap, c))
@@ -783,12 +806,7 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     g.M = M; g.N = N; g.K = 0;
     g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
     int tiles = g.num_m * g.num_n, splits = 1;
-    if (epi.accumulate && tiles < h->num_sms) {
-        splits = h->num_sms / tiles;
-        int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
-    }
+    if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, 8);
     g.kb_per_split = pd_cdiv(g.kb_total, splits);
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
     int units = tiles * g.splits;
@@ -863,13 +881,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
             }
         }
     }
-    if (epi.accumulate && tiles < h->num_sms) {
-        // split-K: spread the contraction over idle SMs, keep >= 8 k-blocks per unit
-        splits = h->num_sms / tiles;
-        int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
-    }
+    if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, 8);   // split-K over idle SMs / partial waves
     // Large tiles-rich problems go to the 2-CTA (cta_group::2) 256x256 kernel; it needs a TMA-addressable C.
     int use2 = h->gemm_2cta && g.tma_store && M >= 512 && N >= 256 && !g.extras_on_split0;
     if (use2) {
@@ -879,12 +891,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
         if (use2) {
             // re-box B for the half tile (128 rows per CTA) — same box as the 1-CTA kernel, so tmB is reused as is
             int splits2 = 1;
-            if (epi.accumulate && tiles2 < pairs_avail) {
-                splits2 = pairs_avail / tiles2;
-                int max_splits = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;
-                if (splits2 > max_splits) splits2 = max_splits;
-                if (splits2 < 1) splits2 = 1;
-            }
+            if (epi.accumulate) splits2 = pick_splits(tiles2, g.kb_total, pairs_avail, 8);
             g.kb_per_split = pd_cdiv(g.kb_total, splits2);
             g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
             int units2 = tiles2 * g.splits;

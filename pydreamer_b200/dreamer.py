@@ -774,18 +774,20 @@ class Dreamer(nn.Module):
         d = self.d
         on_gpu = self._arena.is_cuda
         if not (self.persistent_rssm and self.fp16_forward and self._dp_allows() and (on_gpu or self.ops.is_reference)):
-            return False                  # (data-parallel runs keep the per-step chain)
+            return False
         P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count if on_gpu else 148
         return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and
                 d.G <= min(64, P) and -(-d.D // P) <= 16 and -(-d.Hd // P) <= 16)
 
     def _ov(self, bit):
-        # data-parallel runs keep the single-stream schedule (a 2-GPU run with side streams + the cooperative kernel did
-        # not complete, profiles/r01_h_2gpu_hang.err; not yet root-caused), so does the eager phase timer of bench.py
+        # (the eager phase timer of bench.py needs one stream)
         return bool(self.overlap & bit) and self._arena.is_cuda and self._phase_timer is None and self._dp_allows()
 
-    def _dp_allows(self):       # PD_B200_DP_FEATURES=1 lifts the data-parallel restriction (triage)
-        return self._dp is None or os.environ.get("PD_B200_DP_FEATURES", "0") != "0"
+    def _dp_allows(self):
+        # Data-parallel runs use the SAME schedule as one GPU (side-stream branches, persistent RSSM kernels, graph replay):
+        # the r02 two-GPU triage matrix (profiles/r02_dp_triage.md) completed in every combination.  PD_B200_DP_FEATURES=0
+        # restores round 1's conservative single-stream / per-timestep-chain schedule under data parallelism.
+        return self._dp is None or os.environ.get("PD_B200_DP_FEATURES", "1") != "0"
 
     def _side(self, k):
         key = (k, torch.cuda.current_stream(self._arena.device).cuda_stream)     # one side stream per (purpose, parent)
