@@ -212,6 +212,10 @@ int pd_mask_rows(pd_handle* h, int M, int N, const float* x, long ldx, const flo
                  float* out, long ldo, void* stream);
 /* x[m,:] *= alpha * scale[m / scale_div] */
 int pd_rowscale(pd_handle* h, long M, long N, float* x, long ldx, const float* scale, int scale_div, float alpha, void* stream);
+/* out[m, :] = W[idx[m], :]: `a_mlp` (rssm.py:104, Linear without bias) applied to a one-hot action is a row gather of the
+ * transposed weight W = a_mlp.weight^T [A, Hd] (dreamer.py:197-205: the imagination rollout samples one-hot actions). */
+int pd_gather_rows(pd_handle* h, long M, int N, const int32_t* idx, const float* W, long ldw, float* out, long ldo,
+                   void* stream);
 /* out[r, :] = sum_{i<I} x[r*I + i, :]  (undo the IWAE row expansion, rssm.py:35-41) */
 int pd_group_sum(pd_handle* h, long R, int I, int W, const float* x, long ldx, float* out, long ldo, void* stream);
 int pd_colsum(pd_handle* h, long M, int N, const float* x, long ldx, float* out, void* stream); /* out += */

@@ -313,6 +313,9 @@ class RefOps:
     def scale_by(self, x, scale=None, alpha=1.0):
         x.mul_(alpha * (scale.reshape(-1)[0] if scale is not None else 1.0))
 
+    def gather_rows(self, idx, W, out):
+        out.copy_(W[idx.long().reshape(-1)])
+
     def group_sum(self, x, I, out):
         R, W = out.shape
         out.copy_(x[:, :W].reshape(R, I, W).sum(1))

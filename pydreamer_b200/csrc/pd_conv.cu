@@ -340,9 +340,12 @@ int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, con
                       const float* bias, const float* target, int tgt_div, float* dec, float* diff, float* loss,
                       float* csum, void* stream) {
     int Hout = (Hin - 1) * 2 + k, Wout = (Win - 1) * 2 + k;
-    PD_REQUIRE(h, Cc >= 1 && Cc <= 4, "pd_col2im_imgloss: %d image channels (1..4 supported)", Cc);
-    col2im_imgloss_kernel<4><<<NB, 256, 0, (cudaStream_t)stream>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target,
-                                                                   tgt_div > 0 ? tgt_div : 1, dec, diff, loss, csum);
+    PD_REQUIRE(h, Cc >= 1 && Cc <= 16, "pd_col2im_imgloss: %d image channels (1..16 supported)", Cc);
+    const int div = tgt_div > 0 ? tgt_div : 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Cc <= 4)      col2im_imgloss_kernel<4><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target, div, dec, diff, loss, csum);
+    else if (Cc <= 8) col2im_imgloss_kernel<8><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target, div, dec, diff, loss, csum);
+    else              col2im_imgloss_kernel<16><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target, div, dec, diff, loss, csum);
     PD_CHECK_LAUNCH(h, "col2im_imgloss");
     return PD_OK;
 }

@@ -352,6 +352,16 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 __global__ void inc_kernel(int32_t* c) { *c += 1; }
+// out[m, :] = W[idx[m], :]   (a Linear without bias applied to one-hot rows is a row gather of its transposed weight)
+__global__ void gather_rows_kernel(long M, int N, const int32_t* __restrict__ idx, const float* __restrict__ W, long ldw,
+                                   float* __restrict__ out, long ldo) {
+    const int n4 = N >> 2;
+    GRID_STRIDE(i, M * n4) {
+        const long m = i / n4;
+        const int c = (int)(i % n4) * 4;
+        *reinterpret_cast<float4*>(out + m * ldo + c) = __ldg(reinterpret_cast<const float4*>(W + (long)idx[m] * ldw + c));
+    }
+}
 // x *= alpha * (*scale), exact (no operand rounding); a factor of exactly 1 leaves x untouched, so the launch exits
 // without touching memory (the usual loss.backward() hands over grad_output == 1)
 __global__ void scale_by_kernel(float* __restrict__ x, long n, const float* __restrict__ scale, float alpha) {
@@ -488,6 +498,14 @@ int pd_adamw(pd_handle* h, float* p, const float* g, float* m, float* v, long n,
 int pd_scale_by(pd_handle* h, float* x, long n, const float* scale, float alpha, void* stream) {
     scale_by_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, S(stream)>>>(x, n, scale, alpha);
     PD_CHECK_LAUNCH(h, "scale_by");
+    return PD_OK;
+}
+int pd_gather_rows(pd_handle* h, long M, int N, const int32_t* idx, const float* W, long ldw, float* out, long ldo,
+                   void* stream) {
+    PD_REQUIRE(h, (N % 4) == 0 && (ldw % 4) == 0 && (ldo % 4) == 0 && ((((uintptr_t)W) | ((uintptr_t)out)) & 15) == 0,
+               "pd_gather_rows: N, ldw, ldo must be multiples of 4 and the buffers 16-byte aligned");
+    gather_rows_kernel<<<grid_for(M * (N / 4), 256, h->num_sms), 256, 0, S(stream)>>>(M, N, idx, W, ldw, out, ldo);
+    PD_CHECK_LAUNCH(h, "gather_rows");
     return PD_OK;
 }
 int pd_inc(pd_handle* h, int32_t* counter, void* stream) {

@@ -552,6 +552,11 @@ class Dreamer(nn.Module):
             sh = self._buf(f"decw{li}", kh, kw, co, ci)
             ops.permute4(self._w(w), sh, (2, 3, 1, 0))
             self._decw.append(sh.view(kh * kw * co, ci))
+        # a_mlp^T [A, Hd]: a one-hot action selects one row (imagination rollout, pd_gather_rows)
+        wa = self.wm.core.cell.a_mlp.weight
+        self._waT = self._buf("waT", wa.shape[1], wa.shape[0])
+        ops.permute4(self._w(wa).view(wa.shape[0], wa.shape[1], 1, 1), self._waT.view(wa.shape[1], wa.shape[0], 1, 1),
+                     (1, 0, 2, 3))
         self._weights_dirty = False
 
     def _mlp_params(self, mlp):
@@ -1299,8 +1304,10 @@ class Dreamer(nn.Module):
         cell = self.wm.core.cell
         gru = cell.gru.layers[0]
         ap = self._mlp_params(self.ac.actor)
-        alog = b("dream.alog", H, N, d.Aout)
+        Ap = (d.Aout + 3) // 4 * 4                   # row pitch of the actor outputs: 16-byte rows keep them TMA-addressable
+        alog = b("dream.alog", H, N, Ap)[..., :d.Aout]
         actions = b("dream.actions", H, N, d.A)
+        aidx = b("dream.aidx", N, 1, dtype=torch.int32)
         aa, x, za = b("dream.aa", N, d.Hd), b("dream.x", N, d.Hd), b("dream.za", N, d.Hd)
         mm, rr = b("dream.m", N), b("dream.r", N)
         gi, gh = b("dream.gi", N, 3 * d.D), b("dream.gh", N, 3 * d.D)
@@ -1324,10 +1331,14 @@ class Dreamer(nn.Module):
             fh, fnh = (f16b[i], f16b[i + 1]) if f16 else (None, None)
             self._mlp_fwd(ap, f, alog[i], tag + "actor", rows_total=H * N, row0=i * N, save=True, x16=fh)
             if conf.actor_dist == "onehot":
-                ops.cat_sample(alog[i], noise_actor[i], 1, d.A, actions[i])
+                ops.cat_sample(alog[i], noise_actor[i], 1, d.A, actions[i], idx=aidx)
+                if d.Hd % 4 == 0:
+                    ops.gather_rows(aidx, self._waT, aa)             # a_mlp(one-hot) = one row of a_mlp^T
+                else:
+                    ops.gemm(actions[i], W(cell.a_mlp.weight), aa)
             else:
                 ops.tanh_normal_sample(alog[i], noise_actor[i], actions[i])
-            ops.gemm(actions[i], W(cell.a_mlp.weight), aa)
+                ops.gemm(actions[i], W(cell.a_mlp.weight), aa)
             if f16:
                 ops.gemm_f16(fh[:, d.D:], Wh(cell.z_mlp.weight), x, bias=self._raw(cell.z_mlp.bias), res=aa)
                 ops.ln_elu_fwd(x, self._raw(cell.in_norm.weight), self._raw(cell.in_norm.bias), 1e-3, za, mm, rr, za16)
@@ -1383,9 +1394,10 @@ class Dreamer(nn.Module):
         sums = b("ac.sums", 8, dtype=torch.float64)
         ops.fill(sums.view(torch.float32), 0.0)
         ops.gae_critic(H, N, conf.gamma, conf.lambda_gae, vt, v, rew, tlog, term, adv, agae, target, weight, dv, sums)
-        alog = b("dream.alog", H, N, d.Aout).view(H * N, d.Aout)
+        Ap = (d.Aout + 3) // 4 * 4
+        alog = b("dream.alog", H, N, Ap).view(H * N, Ap)[:, :d.Aout]
         actions = b("dream.actions", H, N, d.A).view(H * N, d.A)
-        dal = b("ac.dalog", H * N, d.Aout)
+        dal = b("ac.dalog", H * N, Ap)[:, :d.Aout]
         if conf.actor_dist == "onehot":
             ops.actor_loss_onehot(conf.entropy, alog, actions, agae, weight, dal, sums[5:7])
         else:

@@ -276,6 +276,13 @@ class NativeOps:
         assert x.is_contiguous()
         self._ck(self.lib.pd_scale_by(self.h, _ptr(x), x.numel(), _ptr(scale), float(alpha), self._s()), "pd_scale_by")
 
+    def gather_rows(self, idx, W, out):
+        """out[m, :] = W[idx[m], :]  (idx int32 [M], W [rows, N], out [M, N])"""
+        M, N = out.shape
+        assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.numel() == M
+        self._ck(self.lib.pd_gather_rows(self.h, M, N, _ptr(idx), _ptr(W), _ld(W), _ptr(out), _ld(out), self._s()),
+                 "pd_gather_rows")
+
     def group_sum(self, x, I, out):
         R, W = out.shape
         self._ck(self.lib.pd_group_sum(self.h, R, I, W, _ptr(x), _ld(x), _ptr(out), _ld(out), self._s()),
