@@ -6,7 +6,10 @@
 //   warp 0      : TMA producer  — cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) into a 6-stage smem ring
 //   warp 1      : MMA issuer    — one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (128x128x8)
 //                                 with the fp32 accumulator tile in TMEM (double buffered, 2 x 128 columns)
-//   warps 2..5  : epilogue      — tcgen05.ld 32x32b.x32 -> registers -> bias/residual/ELU -> global
+//   warps 2..9  : epilogue      — tcgen05.ld 32x32b.x32 -> registers -> bias/residual/ELU -> swizzled smem box -> TMA store
+//                                 (two warps per TMEM lane quarter, alternate 32-column chunks: with a single warp per
+//                                  scheduler the dependent FP chains of bias+ELU+rounding had no latency hiding and
+//                                  small-K tiles were epilogue-bound, profiles/README.md r02)
 // Work units are (m-tile, n-tile, k-split); split-K units add into C with red.global.add.f32.
 //
 // Operand layouts: both operands may be K-major ([rows][K], K contiguous) or MN-major ([K][rows]);
@@ -30,8 +33,9 @@ constexpr int B_BYTES = BN * BK * 4;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;   // 256 (power of two)
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_STAGING = 4 * 2 * 4096;      // per epilogue warp: two 32x32 fp32 swizzled TMA-store boxes
+constexpr int EPI_WARPS = 8;                   // two warps per TMEM lane quarter: they take alternate 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_STAGING = EPI_WARPS * 2 * 4096;   // per epilogue warp: two 32x32 fp32 swizzled TMA-store boxes
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGING;
 
 struct GemmArgs {
@@ -166,7 +170,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
         if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -296,9 +300,11 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // accumulate / split-K, TMA reduce-add (cp.reduce.async.bulk.tensor .add): the copy engine does the
         // addressing, coalescing and M/N edge clipping; the warp issues ~60 instructions per 4 KB of output.
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const int chalf = (warp - 2) >> 2;             // which of the quarter's two warps: chunks chalf, chalf + 2, ...
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
         uint8_t* stg0 = smem + STAGES * STAGE_BYTES + (warp - 2) * (2 * 4096);
+        const bool b_vec = e.bias && ((((uintptr_t)e.bias) & 15) == 0);
         float* stgf = reinterpret_cast<float*>(stg0);     // scalar fallback view (pitch 33 floats fits in 8 KB)
         int sbuf = 0;
         const bool r_vec = e.R && ((e.ldr & 3) == 0) && ((((uintptr_t)e.R) & 15) == 0);
@@ -313,20 +319,28 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = rbase + lane;
             const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
             const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
+            const int nchunk = rbase >= g.M ? 0 : min(BN / 32, (g.N - n0 + 31) / 32);   // chunks with real columns (warp-uniform)
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf; c < nchunk; c += 2) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);     // warp-collective: no divergence above
                 const int col0 = n0 + c * 32;
-                if (rbase >= g.M || col0 >= g.N) continue;           // warp-uniform
                 if (g.tma_store) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     if (extras) {
                         if (e.bias) {
+                            if (b_vec && col0 + 32 <= g.N) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < g.N) ? __ldg(e.bias + col0 + j) : 0.f;
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 q = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+                                    v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += (col0 + j < g.N) ? __ldg(e.bias + col0 + j) : 0.f;
+                            }
                         }
                         if (e.R && row < g.M) {
                             const float* rp = e.R + (long)(row / e.r_div) * e.ldr + col0;
@@ -498,7 +512,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
         if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
         for (int i = 0; i < STAGES2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -590,9 +604,11 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else {
         // ===================== epilogue (warps 2..5, both CTAs; same scheme as the 1-CTA kernel) =====================
         const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
         uint8_t* stg0 = smem + STAGES2 * STAGE2_BYTES + (warp - 2) * (2 * 4096);
+        const bool b_vec = e.bias && ((((uintptr_t)e.bias) & 15) == 0);
         int sbuf = 0;
         const bool r_vec = e.R && ((e.ldr & 3) == 0) && ((((uintptr_t)e.R) & 15) == 0);
         uint32_t leader_tempty[ACC_STAGES];
@@ -609,19 +625,27 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int row = rbase + lane;
             const uint32_t tbase = tmem_base + (uint32_t)(as * BN2) + ((uint32_t)(quarter * 32) << 16);
             const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
+            const int nchunk = rbase >= g.M ? 0 : min(BN2 / 32, (g.N - n0 + 31) / 32);
 #pragma unroll 1
-            for (int c = 0; c < BN2 / 32; ++c) {
+            for (int c = chalf; c < nchunk; c += 2) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);
                 const int col0 = n0 + c * 32;
-                if (rbase >= g.M || col0 >= g.N) continue;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (extras) {
                     if (e.bias) {
+                        if (b_vec && col0 + 32 <= g.N) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += (col0 + j < g.N) ? __ldg(e.bias + col0 + j) : 0.f;
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+                                v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < g.N) ? __ldg(e.bias + col0 + j) : 0.f;
+                        }
                     }
                     if (e.R && row < g.M) {
                         const float* rp = e.R + (long)(row / e.r_div) * e.ldr + col0;
@@ -671,7 +695,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(leader_tempty[as]);      // 4 warps x 2 CTAs -> the leader's MMA issuer
+            if (lane == 0) mbar_arrive_remote(leader_tempty[as]);      // 8 warps x 2 CTAs -> the leader's MMA issuer
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

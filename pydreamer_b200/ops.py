@@ -20,6 +20,9 @@ ACT_NONE, ACT_ELU = 0, 1
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 
 
+_cur_dev = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device    # the raw binding: no lazy-init checks per launch
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -69,7 +72,7 @@ class NativeOps:
     # ------------------------------------------------------------------ plumbing
     def _s(self):
         # kernels launch on the CURRENT device: refuse to enqueue this handle's work on another GPU's context
-        if torch.cuda.current_device() != self._index:
+        if _cur_dev() != self._index:
             raise RuntimeError(f"pydreamer_b200: current CUDA device is {torch.cuda.current_device()} but this model lives on "
                                f"cuda:{self._index}; wrap the call in `with torch.cuda.device({self._index})`")
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
