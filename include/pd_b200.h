@@ -161,8 +161,42 @@ typedef struct pd_rssm_fwd_args {
                                                 * counter, [2..15] seven uint64 phase timers in ns (diagnostic) */
 } pd_rssm_fwd_args;
 int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
-/* Work in progress (not yet run on a GPU): same contract, operands staged as 2-D TMA tiles when PD_B200_K1_STAGING=tma. */
+/* Same contract, operands staged as 2-D TMA tiles (cp.async.bulk.tensor) instead of cp.async rows; selected with
+ * PD_B200_K1_STAGING=tma (validated on B200 in r02: same results, 3 % slower than the cp.async staging at the Atari shape). */
 int pd_rssm_unroll_fwd_v2(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
+
+/* ---- Back-propagation through time of the posterior unroll, one persistent cooperative kernel ------------------------ */
+/* Autograd of rssm.py:21-78,125-153 / rnn.py:60-67 for all T timesteps (csrc/pd_rssm_bptt.cu): per step, descending t,
+ *   dz     = dfeat[t][:, D:] + mask[t+1] * (dx1[t+1] . W_z)                       straight-through sample, rssm.py:147-148
+ *   dpost  = softmax'(post[t]) dz + kl_weight * w[t] * dpost_u[t]                 (+ the KL gradient of dreamer.py:328-343)
+ *   dy2    = LN+ELU backward(post_norm)(dpost . W_pm)                             rssm.py:115-116
+ *   dh     = dy2 . W_ph + dfeat[t][:, :D] + mask[t+1] * (dgh[t+1] . W_hh + dh[t+1] * u[t+1])
+ *   dgi, dgh = GRU gate backward(dh; gates[t], hin[t])                            nn.GRUCell, gate order r|u|n
+ *   dx1    = LN+ELU backward(in_norm)(dgi . W_ih)                                 rssm.py:138-140
+ * Inputs are what pd_rssm_unroll_fwd (or the per-timestep chain) saved; outputs dpost, dy2, dgi, dgh, dx1 [T, BI, .] are the
+ * operands of the batched weight-gradient GEMMs, tf32-rounded when round_out != 0.  LayerNorm affine and the two bias
+ * gradients fed by LayerNorm inputs are ACCUMULATED (+=) into g_*.  Weights come as TRANSPOSED fp16 copies (pd_transpose_to_half):
+ * contraction operands carry 10 mantissa bits on both sides (fp16 weights are exact in tf32; gradients are tf32-rounded fp32),
+ * like the TF32 GEMMs of the launch chain this replaces.  Limits: BI <= 64, Hd <= 1024, C <= 32, D/#SMs <= 16. */
+typedef struct pd_rssm_bwd_args {
+    int T, BI, D, Hd, G, C;
+    int round_out;
+    int ks2, ks6;                              /* set by the library (k-split factors) */
+    float kl_weight;
+    const void *w_pmT16, *w_phT16, *w_hhT16, *w_ihT16, *w_zT16;   /* fp16: [Hd,Z] [D,Hd] [D,3D] [Hd,3D] [Z,Hd] */
+    const float *ln2_g, *ln1_g;                /* post_norm / in_norm weight [Hd] */
+    const float *post, *pin, *y2, *m2, *r2;    /* [T,BI,Z] [T,BI,Hd] [T,BI,Hd] [T,BI] [T,BI] */
+    const float *x1, *za, *m1, *r1;            /* [T,BI,Hd] [T,BI,Hd] [T,BI] [T,BI] */
+    const float *gates, *hin, *mask;           /* [T,BI,4D] (r,u,n,gh_n) [T,BI,D] [T,BI] */
+    const float *dfeat, *dpost_u, *w;          /* [T,BI,D+Z] seeds, [T,BI,Z] unweighted KL gradient, [T,BI] row weights */
+    float *dpost, *dy2, *dgi, *dgh, *dx1;      /* out [T,BI,Z] [T,BI,Hd] [T,BI,3D] [T,BI,3D] [T,BI,Hd] */
+    float *g_ln2_g, *g_ln2_b, *g_b_ph, *g_ln1_g, *g_ln1_b, *g_b_z;   /* += [Hd] each */
+    float *ws_part2, *ws_part6, *ws_part7;     /* workspace [4,BI,Hd] [4,BI,D] [4,BI,Hd] */
+    unsigned int *ws_barrier;                  /* workspace, 16 words, cleared by the call */
+} pd_rssm_bwd_args;
+int pd_rssm_unroll_bwd(pd_handle* h, const pd_rssm_bwd_args* a, void* stream);
+/* dst[n, m] (fp16) = src[m, n] (fp32): the transposed fp16 weight copies pd_rssm_unroll_bwd contracts with. */
+int pd_transpose_to_half(pd_handle* h, int M, int N, const float* src, long lds, void* dst, long ldd, void* stream);
 
 /* ---- KL(post || prior) with balancing, entropies, unweighted grads ------------------------ */
 /* dreamer.py:328-343,369-379.  mode 0 (I == 1): value KL, grads (1-bal)*dKL/dpost and bal*dKL/dprior

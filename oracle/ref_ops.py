@@ -201,6 +201,58 @@ class RefOps:
             idx[s].copy_(k.to(idx.dtype))
             feat[s][:, D:].copy_(F.one_hot(k, C).to(dt).reshape(BI, G * C))
 
+    def transpose_to_half(self, src, dst):
+        dst.copy_(src.t().to(dst.dtype))
+
+    def rssm_unroll_bwd(self, dims, kl_weight, round_out=True, **t):
+        """Torch statement of pd_rssm_unroll_bwd (csrc/pd_rssm_bptt.cu): BPTT of the posterior unroll for all T steps,
+        transposed fp16 weights, same per-step formulas as the chain cat_st_bwd / ln_elu_bwd / gru_bwd of this table."""
+        T, BI, D, Hd, G, C = (int(dims[k]) for k in ("T", "BI", "D", "Hd", "G", "C"))
+        Z = G * C
+        dt = t["dpost"].dtype
+        WpmT, WphT, WhhT, WihT, WzT = (t[k].to(dt) for k in ("w_pmT16", "w_phT16", "w_hhT16", "w_ihT16", "w_zT16"))
+        v3 = lambda k, n: t[k].view(T, BI, n)
+        post, pin, y2, x1, za = v3("post", Z), v3("pin", Hd), v3("y2", Hd), v3("x1", Hd), v3("za", Hd)
+        gates, hin, dfeat, dpu = v3("gates", 4 * D), v3("hin", D), v3("dfeat", D + Z), v3("dpost_u", Z)
+        m2, r2, m1, r1, mask, w = (t[k].view(T, BI) for k in ("m2", "r2", "m1", "r1", "mask", "w"))
+        dpost, dy2, dgi, dgh, dx1 = v3("dpost", Z), v3("dy2", Hd), v3("dgi", 3 * D), v3("dgh", 3 * D), v3("dx1", Hd)
+
+        def ln_bwd(dy, x, y, gamma, mean, rstd, gg, gb, gx):
+            g_ = dy * _elu_grad_from_out(y)
+            xh = (x - mean[:, None]) * rstd[:, None]
+            dxh = g_ * gamma
+            c1, c2 = dxh.mean(-1, keepdim=True), (dxh * xh).mean(-1, keepdim=True)
+            d = rstd[:, None] * (dxh - c1 - xh * c2)
+            gg.add_((g_ * xh).sum(0)); gb.add_(g_.sum(0)); gx.add_(d.sum(0))
+            return d
+
+        dzin_next = dhin_next = None
+        for s in reversed(range(T)):
+            nxt = s + 1 < T
+            dz = dfeat[s][:, D:].clone()
+            if nxt:
+                dz = dz + dzin_next * mask[s + 1][:, None]
+            _, p = _group_softmax(post[s], G, C)
+            dzg = dz.view(BI, G, C)
+            dp = (p * (dzg - (p * dzg).sum(-1, keepdim=True))).reshape(BI, Z) + kl_weight * w[s][:, None] * dpu[s]
+            dpost[s].copy_(dp)
+            dpin = dpost[s] @ WpmT.t()
+            dy2[s].copy_(ln_bwd(dpin, y2[s], pin[s], t["ln2_g"], m2[s], r2[s], t["g_ln2_g"], t["g_ln2_b"], t["g_b_ph"]))
+            dh = dy2[s] @ WphT.t() + dfeat[s][:, :D]
+            if nxt:
+                dh = dh + dhin_next * mask[s + 1][:, None]
+            gt = gates[s].view(BI, 4, D)
+            rg, ug, ng, ghn = gt[:, 0], gt[:, 1], gt[:, 2], gt[:, 3]
+            dn = dh * (1 - ug) * (1 - ng * ng)
+            du = dh * (hin[s] - ng) * ug * (1 - ug)
+            dr = dn * ghn * rg * (1 - rg)
+            dgi[s].copy_(torch.cat([dr, du, dn], 1))
+            dgh[s].copy_(torch.cat([dr, du, dn * rg], 1))
+            dhin_next = dgh[s] @ WhhT.t() + dh * ug
+            dza = dgi[s] @ WihT.t()
+            dx1[s].copy_(ln_bwd(dza, x1[s], za[s], t["ln1_g"], m1[s], r1[s], t["g_ln1_g"], t["g_ln1_b"], t["g_b_z"]))
+            dzin_next = dx1[s] @ WzT.t()
+
     def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]
         _, p = _group_softmax(logits, G, C)

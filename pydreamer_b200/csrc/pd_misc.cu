@@ -52,6 +52,20 @@ __global__ void to_half_kernel(long M, long N, const float* __restrict__ s, long
         d[m * ldd + c] = __float2half_rn(s[m * lds + c]);
     }
 }
+// dst[n][m] = half(src[m][n]): 32x32 tiles through shared memory (both sides coalesced)
+__global__ void transpose_to_half_kernel(int M, int N, const float* __restrict__ s, long lds, __half* __restrict__ d, long ldd) {
+    __shared__ float tile[32][33];
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int m = m0 + r, n = n0 + threadIdx.x;
+        tile[r][threadIdx.x] = (m < M && n < N) ? s[(long)m * lds + n] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int n = n0 + r, m = m0 + threadIdx.x;
+        if (n < N && m < M) d[(long)n * ldd + m] = __float2half_rn(tile[threadIdx.x][r]);
+    }
+}
 __global__ void fill_kernel(float* x, long n, float v) { GRID_STRIDE(i, n) x[i] = v; }
 __global__ void reset_mask_kernel(int T, int B, int I, const uint8_t* __restrict__ reset, float* __restrict__ mask) {
     GRID_STRIDE(i, (long)T * B * I) {
@@ -417,6 +431,12 @@ int pd_colsum(pd_handle* h, long M, int N, const float* x, long ldx, float* out,
 int pd_to_half(pd_handle* h, long M, long N, const float* src, long lds, void* dst, long ldd, void* stream) {
     to_half_kernel<<<grid_for(M * N, 256, h->num_sms), 256, 0, S(stream)>>>(M, N, src, lds, (__half*)dst, ldd);
     PD_CHECK_LAUNCH(h, "to_half");
+    return PD_OK;
+}
+int pd_transpose_to_half(pd_handle* h, int M, int N, const float* src, long lds, void* dst, long ldd, void* stream) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+    transpose_to_half_kernel<<<grid, block, 0, S(stream)>>>(M, N, src, lds, (__half*)dst, ldd);
+    PD_CHECK_LAUNCH(h, "transpose_to_half");
     return PD_OK;
 }
 int pd_fill(pd_handle* h, float* x, long n, float v, void* stream) {

@@ -552,6 +552,15 @@ class Dreamer(nn.Module):
             sh = self._buf(f"decw{li}", kh, kw, co, ci)
             ops.permute4(self._w(w), sh, (2, 3, 1, 0))
             self._decw.append(sh.view(kh * kw * co, ci))
+        if self.persistent_bptt:      # transposed fp16 copies: operands of the persistent BPTT kernel (pd_rssm_unroll_bwd)
+            cell = self.wm.core.cell
+            gru = cell.gru.layers[0]
+            self._k1b_w = {}
+            for name, wgt in (("w_pmT16", cell.post_mlp.weight), ("w_phT16", cell.post_mlp_h.weight),
+                              ("w_hhT16", gru.weight_hh), ("w_ihT16", gru.weight_ih), ("w_zT16", cell.z_mlp.weight)):
+                buf = self._buf("k1b." + name, wgt.shape[1], wgt.shape[0], dtype=torch.float16)
+                ops.transpose_to_half(self._raw(wgt), buf)
+                self._k1b_w[name] = buf
         # a_mlp^T [A, Hd]: a one-hot action selects one row (imagination rollout, pd_gather_rows)
         wa = self.wm.core.cell.a_mlp.weight
         self._waT = self._buf("waT", wa.shape[1], wa.shape[0])
@@ -774,6 +783,26 @@ class Dreamer(nn.Module):
     # The posterior unroll runs as ONE cooperative kernel (csrc/pd_rssm_persistent.cu) when the shape fits its limits
     # (B*I <= 64 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
     persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "1") != "0"
+
+    # BPTT through the posterior unroll as ONE cooperative kernel (csrc/pd_rssm_bptt.cu); PD_B200_PERSISTENT_BPTT=0 selects the
+    # chain of ~12 launches per timestep instead.
+    persistent_bptt = os.environ.get("PD_B200_PERSISTENT_BPTT", "1") != "0"
+
+    def _persistent_bptt_ok(self, BI):
+        d = self.d
+        on_gpu = self._arena.is_cuda
+        if not (self.persistent_bptt and self._dp_allows() and (on_gpu or self.ops.is_reference) and
+                getattr(self, "_k1b_w", None)):
+            return False
+        P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count if on_gpu else 148
+        Z = d.G * d.C
+        ks2 = 4 if Z % 256 == 0 and P >= 4 else 1
+        ks6 = 4 if (3 * d.D) % 256 == 0 and P >= 4 else 1
+        R = max(1, min(4, P // d.G))
+        cd = lambda a_, b_: -(-a_ // b_)
+        return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and Z % 8 == 0 and d.C <= 32 and d.G <= P and
+                cd(BI, R) <= 16 and cd(d.D, P) <= 16 and cd(d.Hd, P // ks2) <= 32 and cd(d.D, P // ks6) <= 64 and
+                cd(d.Hd, P // ks6) <= 32)
 
     def _persistent_rssm_ok(self, BI):
         d = self.d
@@ -1187,9 +1216,6 @@ class Dreamer(nn.Module):
         dhp, dhc = b("bwd.dhp", T, BI, d.D), b("bwd.dhc", BI, d.D)
         dhin, dzin = b("bwd.dhin", T, BI, d.D), b("bwd.dzin", T, BI, d.Z)
         skinny = BI <= 128
-        if skinny:
-            for buf_ in (dpin, dza, dhp, dhin, dzin):
-                ops.fill(buf_, 0.0)
         # ---- encoder backward (as a function of an image-row range)
         geo = ((64, 31, IC, cd), (31, 14, cd, 2 * cd), (14, 6, 2 * cd, 4 * cd), (6, 2, 4 * cd, 8 * cd))
         encgw = {}
@@ -1247,8 +1273,28 @@ class Dreamer(nn.Module):
                 else:
                     ops.permute4(encgw[li].view(co, 4, 4, ci), G(enc[2 * li].weight), (0, 3, 1, 2))
 
-        par = self._ov(2)
-        for t in reversed(range(T)):
+        done = False
+        if self._persistent_bptt_ok(BI):
+            try:
+                ops.rssm_unroll_bwd(
+                    dict(T=T, BI=BI, D=d.D, Hd=d.Hd, G=d.G, C=d.C), conf.kl_weight, True,
+                    ln2_g=self._raw(cell.post_norm.weight), ln1_g=self._raw(cell.in_norm.weight), post=post, pin=pin, y2=y2,
+                    m2=m2, r2=r2, x1=x1, za=za, m1=m1, r1=r1, gates=gates, hin=hin, mask=mask, dfeat=dfeat3,
+                    dpost_u=dpost_u, w=w3, dpost=dpost, dy2=dy2, dgi=dgi, dgh=dgh, dx1=dx1,
+                    g_ln2_g=G(cell.post_norm.weight), g_ln2_b=G(cell.post_norm.bias), g_b_ph=G(cell.post_mlp_h.bias),
+                    g_ln1_g=G(cell.in_norm.weight), g_ln1_b=G(cell.in_norm.bias), g_b_z=G(cell.z_mlp.bias),
+                    ws_part2=b("k1b.part2", 4, BI, d.Hd), ws_part6=b("k1b.part6", 4, BI, d.D),
+                    ws_part7=b("k1b.part7", 4, BI, d.Hd), ws_barrier=b("k1b.bar", 16, dtype=torch.int32), **self._k1b_w)
+                done = True
+            except RuntimeError as e:        # e.g. cooperative launch refused
+                import warnings
+                warnings.warn(f"pydreamer_b200: persistent BPTT kernel unavailable ({e}); using the per-timestep chain")
+                self.persistent_bptt = False
+        par = self._ov(2) and not done
+        if skinny and not done:                     # the chain's split-K GEMMs reduce into pre-cleared outputs
+            for buf_ in (dpin, dza, dhp, dhin, dzin):
+                ops.fill(buf_, 0.0)
+        for t in (() if done else reversed(range(T))):
             nxt = t < T - 1
             ops.cat_st_bwd(post[t], d.G, d.C, dfeat3[t, :, d.D:], dzin[t + 1] if nxt else None,
                            mask[t + 1] if nxt else None, dpost_u[t], w3[t], conf.kl_weight, dpost[t])

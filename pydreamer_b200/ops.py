@@ -44,6 +44,15 @@ class RssmFwdArgs(ctypes.Structure):
                 [("eps", ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS2])
 
 
+class RssmBwdArgs(ctypes.Structure):
+    """struct pd_rssm_bwd_args of include/pd_b200.h (same field order)."""
+    _INTS = ("T", "BI", "D", "Hd", "G", "C", "round_out", "ks2", "ks6")
+    _PTRS = ("w_pmT16", "w_phT16", "w_hhT16", "w_ihT16", "w_zT16", "ln2_g", "ln1_g", "post", "pin", "y2", "m2", "r2", "x1", "za",
+             "m1", "r1", "gates", "hin", "mask", "dfeat", "dpost_u", "w", "dpost", "dy2", "dgi", "dgh", "dx1", "g_ln2_g",
+             "g_ln2_b", "g_b_ph", "g_ln1_g", "g_ln1_b", "g_b_z", "ws_part2", "ws_part6", "ws_part7", "ws_barrier")
+    _fields_ = ([(n, ctypes.c_int) for n in _INTS] + [("kl_weight", ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
+
+
 class NativeOps:
     is_reference = False
 
@@ -202,6 +211,28 @@ class NativeOps:
             self._ck(self.lib.pd_rssm_unroll_fwd_v2(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd_v2")
         else:
             self._ck(self.lib.pd_rssm_unroll_fwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd")
+
+    def rssm_unroll_bwd(self, dims, kl_weight, round_out=True, **t):
+        """Persistent BPTT of the posterior unroll (pd_rssm_unroll_bwd).  dims = dict(T, BI, D, Hd, G, C); every pointer
+        field of the struct is passed as a contiguous tensor by its field name."""
+        a = RssmBwdArgs()
+        for n in ("T", "BI", "D", "Hd", "G", "C"):
+            setattr(a, n, int(dims[n]))
+        a.round_out = int(bool(round_out))
+        a.kl_weight = float(kl_weight)
+        for n in RssmBwdArgs._PTRS:
+            v = t.pop(n)
+            assert v.is_contiguous(), n
+            setattr(a, n, v.data_ptr())
+        assert not t, f"unknown fields {sorted(t)}"
+        self._ck(self.lib.pd_rssm_unroll_bwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_bwd")
+
+    def transpose_to_half(self, src, dst):
+        """dst[n, m] (fp16) = src[m, n] (fp32)"""
+        M, N = src.shape
+        assert dst.shape == (N, M) and dst.dtype == torch.float16
+        self._ck(self.lib.pd_transpose_to_half(self.h, M, N, _ptr(src), _ld(src), _ptr(dst), _ld(dst), self._s()),
+                 "pd_transpose_to_half")
 
     def cat_sample(self, logits, noise, G, C, z, zmask=None, mask_next=None, idx=None, z16=None):
         M = logits.shape[0]

@@ -43,18 +43,23 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "LDTM" in sass                            # tcgen05.ld
 
 
-def test_struct_argument_layout_matches_the_header(tmp_path):
-    """pd_rssm_fwd_args is the one struct in the ABI: the ctypes mirror (ops.RssmFwdArgs) must have the C compiler's
-    size and field offsets for the declaration in include/pd_b200.h."""
+import pytest
+
+
+@pytest.mark.parametrize("cname,pyname", (("pd_rssm_fwd_args", "RssmFwdArgs"), ("pd_rssm_bwd_args", "RssmBwdArgs")))
+def test_struct_argument_layout_matches_the_header(tmp_path, cname, pyname):
+    """The two argument structs of the ABI: the ctypes mirrors (ops.RssmFwdArgs / ops.RssmBwdArgs) must have the C
+    compiler's size and field offsets for the declarations in include/pd_b200.h."""
     import os
 
-    from pydreamer_b200.ops import RssmFwdArgs
+    from pydreamer_b200 import ops as _ops_mod
 
+    RssmFwdArgs = getattr(_ops_mod, pyname)
     fields = [n for n, _ in RssmFwdArgs._fields_]
     src = tmp_path / "layout.c"
-    body = "".join(f'    printf("{n} %zu\\n", offsetof(pd_rssm_fwd_args, {n}));\n' for n in fields)
+    body = "".join(f'    printf("{n} %zu\\n", offsetof({cname}, {n}));\n' for n in fields)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pd_b200.h"\nint main(void) {\n'
-                   '    printf("sizeof %zu\\n", sizeof(pd_rssm_fwd_args));\n' + body + "    return 0;\n}\n")
+                   f'    printf("sizeof %zu\\n", sizeof({cname}));\n' + body + "    return 0;\n}\n")
     exe = tmp_path / "layout"
     inc = os.path.join(os.path.dirname(os.path.abspath(_native.HEADER)))
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)       # the header is plain C
@@ -63,6 +68,16 @@ def test_struct_argument_layout_matches_the_header(tmp_path):
     assert list(out) == fields                                                      # same fields, same order
     for n in fields:
         assert int(out[n]) == getattr(RssmFwdArgs, n).offset, n
+
+
+def test_sass_of_the_persistent_bptt_kernel():
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "rssm_unroll_bwd_kernel", _native.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    if "HMMA" not in sass:
+        sass = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTMALDG.2D" in sass                  # operands staged by TMA (cp.async.bulk.tensor.2d)
+    assert "HMMA.1688.F32.TF32" in sass          # mma.sync.m16n8k8 tf32
+    assert "SYNCS" in sass and "LDSM" in sass    # mbarrier pipeline, ldmatrix weight fragments
 
 
 def test_sass_of_the_persistent_rssm_kernel():

@@ -20,11 +20,12 @@ def ref_ops():
     pd_ops.set_ops_for_testing(None)
 
 
-def run_model(case, fp16_forward=False, persistent_rssm=False, direct_conv1=False):
+def run_model(case, fp16_forward=False, persistent_rssm=False, direct_conv1=False, persistent_bptt=False):
     fx, conf, obs, state, noise = build_case(case)
     model = Dreamer(conf)
     model.fp16_forward = fp16_forward
     model.persistent_rssm = persistent_rssm
+    model.persistent_bptt = persistent_bptt
     model.direct_conv1 = direct_conv1
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
@@ -91,6 +92,25 @@ def test_persistent_rssm_branch_of_the_schedule(ref_ops, case):
     for k, want in fx["grad_norms"].items():
         if k.startswith("wm.") and want > 1e-6:
             assert abs(float(named[k].grad.double().norm()) - want) <= 2e-2 * want + 1e-7, k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_persistent_bptt_branch_of_the_schedule(ref_ops, case):
+    """The host branch that hands BPTT through the posterior unroll to ONE call (pd_rssm_unroll_bwd on the GPU, its torch
+    twin here): same goldens; the recurrent weights enter as transposed fp16 copies (10 mantissa bits, like the TF32 chain
+    on the GPU), which moves world-model gradients by < 2e-3."""
+    fx, conf, model, opts, losses, out_state, metrics, tensors = run_model(case, persistent_bptt=True)
+    T, BI = conf.batch_length, conf.batch_size * conf.iwae_samples
+    assert model._persistent_bptt_ok(BI)
+    assert ("bwd.dhin", (T, BI, conf.deter_dim), torch.float32) in model._ws                 # allocated ...
+    assert float(model._buf("bwd.dpost", T, BI, conf.stoch_dim * conf.stoch_discrete).abs().sum()) > 0
+    for i, (got, want) in enumerate(zip(losses, fx["losses"])):
+        assert abs(float(got.detach().reshape(-1)[0]) - want) <= 2e-5 * max(1.0, abs(want)), (i, got, want)
+    named = dict(model.named_parameters())
+    for k, want in fx["grad_norms"].items():
+        got = float(named[k].grad.double().norm())
+        tol = 2e-3 if k.startswith("wm.") else 2e-4
+        assert abs(got - want) <= tol * max(want, 1e-6) + 1e-8, (k, got, want)
 
 
 def test_direct_first_conv_branch_of_the_schedule(ref_ops):

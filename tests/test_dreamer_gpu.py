@@ -23,6 +23,7 @@ def run_gpu(case, impl, rounding, persistent=False):
     model = Dreamer(conf).to(DEV)
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     model.persistent_rssm = persistent        # posterior unroll as one cooperative kernel (pd_rssm_unroll_fwd)
+    model.persistent_bptt = persistent        # ... and its BPTT as one cooperative kernel (pd_rssm_unroll_bwd)
     model.fp16_forward = (impl == 0)          # the exact arm keeps every GEMM in fp32
     model.implicit_conv = (impl == 0)         # ... and uses the explicit im2col + SIMT GEMM path
     model._ensure_arena()
@@ -64,6 +65,7 @@ def test_product_arm_tcgen05_teacher_forced_against_oracle(case, persistent):
     fx, conf, obs, state, noise, model, losses, out_state, metrics, tensors = run_gpu(case, impl=0, rounding=True,
                                                                                       persistent=persistent)
     assert model._persistent_rssm_ok(conf.batch_size * conf.iwae_samples) == persistent
+    assert model._persistent_bptt_ok(conf.batch_size * conf.iwae_samples) == persistent
     T, B, I, H = conf.batch_length, conf.batch_size, conf.iwae_samples, conf.imag_horizon
     N, G, C, D = T * B * I, conf.stoch_dim, conf.stoch_discrete, conf.deter_dim
     post_idx = model._buf("rssm.idx", T, B * I, G, dtype=torch.int32).long().cpu()
@@ -229,3 +231,62 @@ def test_persistent_rssm_kernel_matches_the_per_step_chain_at_full_size():
             x, y = x[..., :D], y[..., :D]
         err = float((x - y).abs().max() / (x.abs().max() + 1e-12))
         assert err < 2e-3, (k, err)
+
+
+@pytest.mark.parametrize("preset,over", (("atari", {}), ("dmc", {}), ("atari_iwae", dict(batch_size=16))),
+                         ids=("atari", "dmc", "atari_iwae4_b16"))
+def test_persistent_bptt_kernel_matches_the_per_step_chain_at_full_size(preset, over):
+    """pd_rssm_unroll_bwd (one cooperative kernel: TMA-staged fp16 weight tiles, tf32 mma.sync) against the chain of
+    per-timestep launches (TF32 tcgen05 GEMMs + row-wise kernels) on the SAME forward pass: both contract 10-bit operands,
+    so every tensor the kernel writes agrees with the chain's to accumulation order and weight rounding (fp16 vs tf32
+    rounding of the same master weight)."""
+    from pydreamer_b200.config import make_conf
+    from pydreamer_b200.replay import synthetic_batch
+    from oracle.weights import seeded_state_dict
+
+    conf = make_conf(preset, device=DEV, **over)
+    T, B, I, H = conf.batch_length, conf.batch_size, conf.iwae_samples, conf.imag_horizon
+    D, G, C, A = conf.deter_dim, conf.stoch_dim, conf.stoch_discrete, conf.action_dim
+    Z, BI, N, Hd = G * C, B * I, T * B * I, conf.hidden_dim
+    obs = synthetic_batch(conf, seed=3, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    state = (torch.tanh(torch.randn(BI, D, device=DEV, generator=g)), torch.zeros(BI, Z, device=DEV))
+    noise = dict(post=torch.empty(T, BI, Z, device=DEV).exponential_(generator=g),
+                 prior=torch.empty(H, N, Z, device=DEV).exponential_(generator=g))
+    noise["actor"] = (torch.empty(H, N, A, device=DEV).exponential_(generator=g) if conf.actor_dist == "onehot"
+                      else torch.empty(H, N, A, device=DEV).normal_(generator=g))
+    got = {}
+    for mode in (False, True):
+        model = Dreamer(conf).to(DEV)
+        model.load_state_dict(seeded_state_dict(model.state_dict(), 11))
+        model.persistent_bptt = mode
+        losses, *_ = model.training_step(obs, state, noise=noise)
+        for l in losses:
+            l.backward()
+        torch.cuda.synchronize()
+        assert model._persistent_bptt_ok(BI) == mode
+        names = dict(dpost=("bwd.dpost", (T, BI, Z)), dy2=("bwd.dy2", (T, BI, Hd)), dgi=("bwd.dgi", (T, BI, 3 * D)),
+                     dgh=("bwd.dgh", (T, BI, 3 * D)), dx1=("bwd.dx1", (T, BI, Hd)))
+        got[mode] = {k: model._buf(n, *shp).clone() for k, (n, shp) in names.items()}
+        got[mode]["idx"] = model._buf("rssm.idx", T, BI, G, dtype=torch.int32).clone()
+        cell = model.wm.core.cell
+        got[mode]["grads"] = {k: p.grad.detach().clone() for k, p in model.named_parameters()
+                              if k.startswith("wm.core.") or k.startswith("wm.encoder.")}
+        del model
+    a, b = got[False], got[True]
+    assert torch.equal(a["idx"], b["idx"])                     # same forward pass, same samples
+    worst = {}
+    for k in ("dpost", "dy2", "dgi", "dgh", "dx1"):
+        x, y = a[k].double(), b[k].double()
+        worst[k] = (float((x - y).norm() / (x.norm() + 1e-30)), float((x - y).abs().max() / (x.abs().max() + 1e-30)))
+    gw = {}
+    for k in a["grads"]:
+        x, y = a["grads"][k].double(), b["grads"][k].double()
+        gw[k] = float((x - y).norm() / (x.norm() + 1e-30))
+    kworst = max(gw, key=gw.get)
+    print(f"[{preset}] persistent BPTT vs chain (l2-relative, worst-element/max):", {k: f"{v[0]:.1e}/{v[1]:.1e}" for k, v in worst.items()},
+          f"; worst parameter gradient {kworst} {gw[kworst]:.1e}")
+    for k, (l2, mx) in worst.items():
+        assert l2 < 1e-3 and mx < 3e-3, (k, l2, mx)
+    for k, v in gw.items():
+        assert v < 1.5e-3, (k, v)
