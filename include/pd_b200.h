@@ -131,14 +131,17 @@ int pd_cat_st_bwd(pd_handle* h, int M, int G, int C, const float* logits, long l
                   float* dlogits, long lddl, void* stream);
 
 /* ---- persistent RSSM posterior unroll (rssm.py:21-78 RSSMCore.forward, 125-153 RSSMCell.forward) -------------
- * ONE cooperative kernel walks all T timesteps: per step { z_mlp as a gather over the sampled one-hot + a_mlp term
- * -> LayerNorm+ELU -> GRU gates (fp16 mma.sync tensor-core contractions, fp32 accumulate) -> post_mlp_h + embed term
- * -> LayerNorm+ELU -> post_mlp -> categorical sample }, with grid-wide barriers between the dependent phases instead
- * of kernel boundaries; every CTA owns a fixed slice of hidden units / features / latent groups for the whole
- * sequence.  Writes exactly the buffers the chain of per-step kernels writes (the backward reads them).
+ * ONE cooperative kernel walks all T timesteps (csrc/pd_rssm_fwd3.cu): per step { z_mlp as a gather over the sampled
+ * one-hot + a_mlp term -> LayerNorm+ELU -> GRU gates -> post_mlp_h + embed term -> LayerNorm+ELU -> post_mlp ->
+ * categorical sample }, with grid-wide barriers between the dependent phases instead of kernel boundaries; every CTA owns
+ * a fixed slice of hidden units / features / latent groups for the whole sequence.  Operands are staged by a producer
+ * warp with TMA into an mbarrier ring (weights of the next phase are prefetched across the grid barrier), contractions are
+ * fp16 mma.sync with fp32 accumulation, the recurrent products over K = D are split in four k-slices.  Writes exactly the
+ * buffers the chain of per-step kernels writes (the backward reads them).
  * Caller prepares: hin[0] / zin[0] (masked in_state), x1[0] (pre-norm input of step 0 incl. bias and action term),
- * aa / ea (action and embed projections hoisted over T), fp16 weight copies.  Limits: BI <= 64, Hd <= 1024,
- * C <= 32, G <= #CTAs, D and Hd <= 16 * #CTAs and multiples of 8; otherwise PD_ERR_UNSUPPORTED (use the chain). */
+ * aa / ea (action and embed projections hoisted over T), fp16 weight copies incl. the TRANSPOSED z_mlp weight ws_wzT16
+ * (pd_transpose_to_half).  Limits: BI <= 64, Hd <= 1024, C <= 32, G <= #CTAs, D <= 16 * #CTAs, D and Hd multiples of 8;
+ * otherwise PD_ERR_UNSUPPORTED (use the chain). */
 typedef struct pd_rssm_fwd_args {
     int T, BI, I, D, Hd, G, C;                 /* rows BI = B*I; Z = G*C; feat row pitch F = D + Z */
     const void *w_z16, *w_ih16, *w_hh16, *w_ph16, *w_pm16;   /* fp16 [Hd,Z] [3D,Hd] [3D,D] [Hd,D] [Z,Hd] */
@@ -155,15 +158,12 @@ typedef struct pd_rssm_fwd_args {
     float *y2, *pin, *m2, *r2;                 /* [T,BI,Hd] x2, [T,BI] x2 */
     float *post;                               /* [T,BI,Z] posterior logits */
     int32_t *idx;                              /* [T,BI,G] sampled classes */
-    void *ws_wzT16;                            /* workspace fp16 [Z,Hd] */
+    void *ws_wzT16;                            /* in: fp16 [Z,Hd] = z_mlp.weight^T (pd_transpose_to_half) */
     void *ws_za16, *ws_h16, *ws_pin16;         /* workspace fp16 [BI,Hd] [BI,D] [BI,Hd] */
-    unsigned int *ws_barrier;                  /* workspace, 16 words, 8-byte aligned, cleared by the call: [0] barrier
-                                                * counter, [2..15] seven uint64 phase timers in ns (diagnostic) */
+    unsigned int *ws_barrier;                  /* workspace, 16 words, 8-byte aligned, cleared by the call: [0] barrier counter */
+    float *ws_ghpart, *ws_y2part;              /* workspace [4,BI,3D] [4,BI,Hd]: k-slice partial sums of the recurrent products */
 } pd_rssm_fwd_args;
 int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
-/* Same contract, operands staged as 2-D TMA tiles (cp.async.bulk.tensor) instead of cp.async rows; selected with
- * PD_B200_K1_STAGING=tma (validated on B200 in r02: same results, 3 % slower than the cp.async staging at the Atari shape). */
-int pd_rssm_unroll_fwd_v2(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
 
 /* ---- Back-propagation through time of the posterior unroll, one persistent cooperative kernel ------------------------ */
 /* Autograd of rssm.py:21-78,125-153 / rnn.py:60-67 for all T timesteps (csrc/pd_rssm_bptt.cu): per step, descending t,

@@ -151,7 +151,7 @@ class RefOps:
         out.copy_(F.elu(y).permute(0, 2, 3, 1).reshape(out.shape))
 
     def rssm_unroll_fwd(self, dims, eps, **t):
-        """Torch statement of pd_rssm_unroll_fwd (csrc/pd_rssm_persistent.cu; rssm.py:21-78, 125-153): the whole posterior
+        """Torch statement of pd_rssm_unroll_fwd (csrc/pd_rssm_fwd3.cu; rssm.py:21-78, 125-153): the whole posterior
         unroll in one call, fp16 weights, LayerNorm outputs and h rounded to fp16 (they are the tensor-core operands)."""
         T, BI, I, D, Hd, G, C = (int(dims[k]) for k in ("T", "BI", "I", "D", "Hd", "G", "C"))
         B = BI // I

@@ -26,22 +26,15 @@
 //       P6/7   (row-group, k-slice): dh_{t-1} partials = dgh_t W_hh ; dza partials = dgi_t W_ih   (K = 3D split in 4)
 //       P8     batch-row owners    : LayerNorm+ELU backward (in_norm)    -> dx1_t
 //     K-split partial sums are added by their consumers (row owners / unit owners), which costs no extra barrier.
-#include "pd_common.cuh"
-#include <cuda_fp16.h>
+#include "pd_k1_pipe.cuh"
 
 namespace {
+using namespace k1;
 
-constexpr int NCW = 8;                         // consumer warps
-constexpr int NCT = 32 * NCW;                  // consumer threads
-constexpr int NT = NCT + 32;                   // + producer warp
-constexpr int BROWS = 64;                      // batch rows staged per box (B*I <= 64)
-constexpr int KB = 64;                         // k per stage: 64 halfs of weights (128 B rows) = two 32-float boxes of X
-constexpr int MAXT = 6;                        // weight tiles (16 rows) per stage
-constexpr int A_TILE = 16 * 128;               // 2 KB
-constexpr int X_BOX = BROWS * 128;             // 8 KB: 64 rows x 32 floats
-constexpr int STAGE_BYTES = MAXT * A_TILE + 4 * X_BOX;     // 44 KB
-constexpr int NSTAGE = 4;
-constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;               // full[NSTAGE], empty[NSTAGE]
+constexpr int MAXT = 6;                        // weight tiles (16 rows) per stage: 4 of W_hh^T + 2 of W_ih^T in phase P6/7
+typedef Ring<MAXT, 4> RingB;                   // + up to four 64-row x 32-float boxes of the gradient operand (fp32): 44 KB
+typedef Job<MAXT> JobB;
+constexpr int OFF_BAR = RingB::BYTES;                       // full[NSTAGE], empty[NSTAGE]
 constexpr int OFF_SH = OFF_BAR + 128;                       // 64 floats: block reductions
 constexpr int OFF_DHC = OFF_SH + 256;                       // [16][BROWS] floats: dh*u of my hidden units (carry to t-1)
 constexpr int OFF_DZ = OFF_DHC + 16 * BROWS * 4;            // [16][32] floats: dzin of my (rows, latent group)
@@ -53,197 +46,6 @@ struct BwdMaps {
     CUtensorMap dpost, dy2, dgh, dgi, dx1;     // fp32 [(T*BI)][K], box {32 floats, 64 rows}, SWIZZLE_128B
     CUtensorMap dx1_16;                        // same tensor, box {32 floats, 16 rows}
 };
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0, spins = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(s_u32(bar)), "r"(parity) : "memory");
-        if (!done && ++spins > (1u << 26)) __trap();            // a broken pipeline must not hang the GPU
-    }
-}
-__device__ __forceinline__ void tma_box(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(s_u32(dst)), "l"((uint64_t)map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t h_lo(uint32_t v) { return __float_as_uint(__half2float(__ushort_as_half((unsigned short)(v & 0xffffu)))); }
-__device__ __forceinline__ uint32_t h_hi(uint32_t v) { return __float_as_uint(__half2float(__ushort_as_half((unsigned short)(v >> 16)))); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
-
-// Block-wide sum over the 256 consumer threads (result valid in all of them).
-__device__ __forceinline__ float cons_sum(float v, float* sh) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    v = pd_warp_sum(v);
-    cons_sync();
-    if (lane == 0) sh[w] = v;
-    cons_sync();
-    float r = lane < NCW ? sh[lane] : 0.f;
-    return pd_warp_sum(r);
-}
-
-// Grid-wide barrier among the consumer threads of all CTAs (monotonic counter, cleared by the host before the launch).
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
-    cons_sync();
-    epoch += 1;
-    if (threadIdx.x == 0) {
-        const unsigned target = epoch * gridDim.x;
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        unsigned spins = 0;
-        while (ld_acquire(ctr) < target) {
-            if (++spins > (1u << 24)) __trap();
-        }
-        __threadfence();
-    }
-    cons_sync();
-}
-// Producer side: wait until barrier number `epoch` has completed, then make what the other CTAs published through the
-// generic proxy visible to this thread's TMA (async proxy) reads.
-__device__ __forceinline__ void producer_wait_barrier(const unsigned* ctr, unsigned epoch) {
-    const unsigned target = epoch * gridDim.x;
-    unsigned spins = 0;
-    while (ld_acquire(ctr) < target) {
-        if (++spins > (1u << 24)) __trap();
-    }
-    __threadfence();
-    asm volatile("fence.proxy.async;" ::: "memory");
-}
-
-struct Ring {                       // both sides count stages identically: slot = n % NSTAGE, parity = (n / NSTAGE) & 1
-    uint8_t* smem;
-    uint64_t* full;
-    uint64_t* empty;
-    uint32_t n;
-    __device__ __forceinline__ uint8_t* stage(uint32_t i) const { return smem + (i % NSTAGE) * STAGE_BYTES; }
-};
-
-// One contraction job of this CTA for one phase: `ntile` weight tiles out of `wmap` (tile i = rows [row0[i], row0[i]+16)),
-// `nkb` k-blocks of 64 starting at column kcol0; gradient operand boxes: X map 0 for tiles with xsel == 0, X map 1 otherwise.
-struct Job {
-    const CUtensorMap* wmap[MAXT];
-    int row0[MAXT];
-    int ntile;
-    const CUtensorMap* xmap[2];
-    int nx;                          // 1 or 2 gradient operands
-    int xrow0;                       // row coordinate of the box (t * BI [+ sub-range start])
-    int xrows;                       // 64 or 16 rows per box
-    int kcol0, nkb;
-    int x2_from;                     // second operand only differs from the first for k >= x2_from (else the first is reused)
-};
-
-__device__ __forceinline__ bool job_needs_x2(const Job& j, int kb) { return j.nx == 2 && j.kcol0 + (kb + 1) * KB > j.x2_from; }
-__device__ __forceinline__ uint32_t job_bytes(const Job& j, int kb) {
-    const uint32_t xb = (uint32_t)j.xrows * 128u * 2u;
-    return (uint32_t)j.ntile * A_TILE + xb * (job_needs_x2(j, kb) ? 2u : 1u);
-}
-
-// Producer: weights of the first stages are requested before the grid barrier `wait_epoch` (0 = no barrier to wait for),
-// gradient boxes after it.
-__device__ void produce(Ring& ring, const Job& j, const unsigned* ctr, unsigned wait_epoch) {
-    const int npre = j.nkb < NSTAGE ? j.nkb : NSTAGE;
-    auto weights = [&](int kb) {
-        const uint32_t n = ring.n + kb;
-        mbar_wait(ring.empty + n % NSTAGE, ((n / NSTAGE) & 1) ^ 1);
-        mbar_expect_tx(ring.full + n % NSTAGE, job_bytes(j, kb));
-        uint8_t* st = ring.stage(n);
-        for (int i = 0; i < j.ntile; ++i) tma_box(j.wmap[i], ring.full + n % NSTAGE, st + i * A_TILE, j.kcol0 + kb * KB, j.row0[i]);
-    };
-    auto xboxes = [&](int kb) {
-        const uint32_t n = ring.n + kb;
-        uint8_t* st = ring.stage(n) + MAXT * A_TILE;
-        const int kf = j.kcol0 + kb * KB;                           // column (floats) of this k-block
-        tma_box(j.xmap[0], ring.full + n % NSTAGE, st, kf, j.xrow0);
-        tma_box(j.xmap[0], ring.full + n % NSTAGE, st + X_BOX, kf + 32, j.xrow0);
-        if (job_needs_x2(j, kb)) {
-            tma_box(j.xmap[1], ring.full + n % NSTAGE, st + 2 * X_BOX, kf, j.xrow0);
-            tma_box(j.xmap[1], ring.full + n % NSTAGE, st + 3 * X_BOX, kf + 32, j.xrow0);
-        }
-    };
-    for (int kb = 0; kb < npre; ++kb) weights(kb);
-    if (wait_epoch) producer_wait_barrier(ctr, wait_epoch);
-    for (int kb = 0; kb < npre; ++kb) xboxes(kb);
-    for (int kb = npre; kb < j.nkb; ++kb) { weights(kb); xboxes(kb); }
-    ring.n += j.nkb;
-}
-
-// Consumer: this warp accumulates TW weight tiles (tile0 ..) x NW8 n8-tiles of batch rows (n8_0 ..) over all k-blocks of
-// the job; xsel = which gradient operand its tiles contract with.  Warps without work pass TW = 0 (they still walk the ring).
-// acc[i][j][4]: mma C fragment of (tile i, n8-tile j): rows g, g+8 of the tile, batch columns 2t, 2t+1 of the n8-tile.
-template <int TW, int NW8>
-__device__ void consume(Ring& ring, const Job& j, int tile0, int n8_0, int xsel, bool active, float (&acc)[TW > 0 ? TW : 1][NW8 > 0 ? NW8 : 1][4]) {
-    const int lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int i = 0; i < (TW > 0 ? TW : 1); ++i)
-#pragma unroll
-        for (int jn = 0; jn < (NW8 > 0 ? NW8 : 1); ++jn)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[i][jn][e] = 0.f;
-    for (int kb = 0; kb < j.nkb; ++kb) {
-        const uint32_t n = ring.n + kb;
-        mbar_wait(ring.full + n % NSTAGE, (n / NSTAGE) & 1);
-        if (TW > 0 && active) {
-            const uint8_t* st = ring.stage(n);
-            const bool x2 = job_needs_x2(j, kb);
-            const uint8_t* xb = st + MAXT * A_TILE + ((xsel && x2) ? 2 * X_BOX : 0);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                    // four k16 steps of the 64-wide block
-                uint32_t a[TW > 0 ? TW : 1][4];
-#pragma unroll
-                for (int i = 0; i < TW; ++i) {
-                    const int r = lane & 15;
-                    ldsm_x4(s_u32(st + (tile0 + i) * A_TILE + r * 128 + (((ks * 2 + (lane >> 4)) ^ (r & 7)) << 4)), a[i][0],
-                            a[i][1], a[i][2], a[i][3]);
-                }
-                const uint8_t* box = xb + (ks >> 1) * X_BOX;    // two k16 steps per 32-float box
-                const int kk0 = (ks & 1) * 16;
-#pragma unroll
-                for (int jn = 0; jn < NW8; ++jn) {
-                    const int row = (n8_0 + jn) * 8 + g;
-                    const uint8_t* rp = box + row * 128;
-                    const float2 fa = *reinterpret_cast<const float2*>(rp + ((((kk0 + 2 * t) >> 2) ^ (row & 7)) << 4) + ((2 * t) & 3) * 4);
-                    const float2 fb = *reinterpret_cast<const float2*>(rp + ((((kk0 + 2 * t + 8) >> 2) ^ (row & 7)) << 4) + ((2 * t) & 3) * 4);
-#pragma unroll
-                    for (int i = 0; i < TW; ++i) {
-                        // even k (2t, 2t+8) from the low halves, odd k (2t+1, 2t+9) from the high halves
-                        mma_tf32(acc[i][jn], h_lo(a[i][0]), h_lo(a[i][1]), h_lo(a[i][2]), h_lo(a[i][3]), __float_as_uint(fa.x),
-                                 __float_as_uint(fb.x));
-                        mma_tf32(acc[i][jn], h_hi(a[i][0]), h_hi(a[i][1]), h_hi(a[i][2]), h_hi(a[i][3]), __float_as_uint(fa.y),
-                                 __float_as_uint(fb.y));
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ring.empty + n % NSTAGE);
-    }
-    ring.n += j.nkb;
-}
 
 __device__ __forceinline__ float rnd(float x, int on) { return on ? pd_tf32(x) : x; }
 
@@ -260,15 +62,8 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
     const int T = a.T, BI = a.BI, D = a.D, Hd = a.Hd, G = a.G, C = a.C, Z = G * C, F = D + Z, D3 = 3 * D;
     const int rnd_on = a.round_out;
 
-    Ring ring;
-    ring.smem = smem;
-    ring.full = (uint64_t*)(smem + OFF_BAR);
-    ring.empty = ring.full + NSTAGE;
-    ring.n = 0;
-    if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(ring.full + i, 1); mbar_init(ring.empty + i, NCW); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    RingB ring;
+    ring.init(smem, (uint64_t*)(smem + OFF_BAR));
     for (int i = tid; i < 16 * BROWS; i += NT) dhc[i] = 0.f;
     for (int i = tid; i < 16 * 32; i += NT) dzs[i] = 0.f;
     __syncthreads();
@@ -292,26 +87,26 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
     const int kslice2 = Z / KS2, kslice6 = D3 / KS6;
 
     auto job_p2 = [&](int t) {
-        Job j; j.ntile = nt2; j.nx = 1; j.xmap[0] = &maps.dpost; j.xmap[1] = &maps.dpost; j.xrow0 = t * BI; j.xrows = BROWS;
+        JobB j; j.xf16 = 0; j.ntile = nt2; j.nx = 1; j.xmap[0] = &maps.dpost; j.xmap[1] = &maps.dpost; j.xrow0 = t * BI; j.xrows = BROWS;
         j.kcol0 = ks2 * kslice2; j.nkb = nt2 ? (kslice2 + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wpmT; j.row0[i] = f2_0 + 16 * i; }
         return j;
     };
     auto job_p4 = [&](int t) {
-        Job j; j.ntile = nu4 > 0 ? 1 : 0; j.nx = 1; j.xmap[0] = &maps.dy2; j.xmap[1] = &maps.dy2; j.xrow0 = t * BI; j.xrows = BROWS;
+        JobB j; j.xf16 = 0; j.ntile = nu4 > 0 ? 1 : 0; j.nx = 1; j.xmap[0] = &maps.dy2; j.xmap[1] = &maps.dy2; j.xrow0 = t * BI; j.xrows = BROWS;
         j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wphT; j.row0[i] = u4_0; }
         return j;
     };
     auto job_p6 = [&](int t) {
-        Job j; j.ntile = (nt6h || nt6z) ? 6 : 0; j.nx = 2; j.xmap[0] = &maps.dgh; j.xmap[1] = &maps.dgi; j.xrow0 = t * BI; j.xrows = BROWS;
+        JobB j; j.xf16 = 0; j.ntile = (nt6h || nt6z) ? 6 : 0; j.nx = 2; j.xmap[0] = &maps.dgh; j.xmap[1] = &maps.dgi; j.xrow0 = t * BI; j.xrows = BROWS;
         j.kcol0 = ks6 * kslice6; j.nkb = j.ntile ? (kslice6 + KB - 1) / KB : 0; j.x2_from = 2 * D;   // dgi == dgh for the r, u gates
         for (int i = 0; i < 4; ++i) { j.wmap[i] = &maps.whhT; j.row0[i] = u6_0 + 16 * i; }
         for (int i = 0; i < 2; ++i) { j.wmap[4 + i] = &maps.wihT; j.row0[4 + i] = f6_0 + 16 * i; }
         return j;
     };
     auto job_p9 = [&](int t) {
-        Job j; j.ntile = in9 ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = &maps.dx1_16; j.xmap[1] = &maps.dx1_16;
+        JobB j; j.xf16 = 0; j.ntile = in9 ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = &maps.dx1_16; j.xmap[1] = &maps.dx1_16;
         j.xrow0 = t * BI + b9_0; j.xrows = 16;
         j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wzT; j.row0[i] = g9 * C + 16 * i; }
@@ -324,10 +119,10 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
             unsigned epoch = 0;
             for (int t = T - 1; t >= 0; --t) {
                 // barriers of a step, in order: after P1 (1), after P2 (2), after P3 (3), after P4 (4), after P6/7 (5), after P8 (6)
-                { const Job j = job_p2(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 1); }
-                { const Job j = job_p4(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 3); }
-                { const Job j = job_p6(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 4); }
-                if (t > 0) { const Job j = job_p9(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 6); }
+                { const JobB j = job_p2(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 1); }
+                { const JobB j = job_p4(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 3); }
+                { const JobB j = job_p6(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 4); }
+                if (t > 0) { const JobB j = job_p9(t); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 6); }
                 epoch += 6;
             }
         }
@@ -402,10 +197,10 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
 
         // ---------------- P2 (row group x k slice): dpin partials = dpost_t . W_pm
         {
-            const Job j = job_p2(t);
+            const JobB j = job_p2(t);
             float acc[2][1][4];
             const bool act = warp * 8 < BI;
-            consume<2, 1>(ring, j, 0, warp, 0, act && j.nkb > 0, acc);
+            consume_tf32<2, 1>(ring, j, 0, warp, 0, act && j.nkb > 0, acc);
             if (act && j.nkb > 0) {
                 const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
@@ -438,10 +233,10 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
 
         // ---------------- P4 (hidden-unit owners): dh = dy2_t . W_ph + dfeat_h + carry ; GRU gate backward -> dgi_t, dgh_t
         {
-            const Job j = job_p4(t);
+            const JobB j = job_p4(t);
             float acc[1][1][4];
             const bool act = warp * 8 < BI;
-            consume<1, 1>(ring, j, 0, warp, 0, act && j.nkb > 0, acc);
+            consume_tf32<1, 1>(ring, j, 0, warp, 0, act && j.nkb > 0, acc);
             if (act && j.nkb > 0) {
                 const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
@@ -475,12 +270,12 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
 
         // ---------------- P6/7 (row group x k slice): dh_{t-1} partials = dgh_t . W_hh ; dza partials = dgi_t . W_ih
         {
-            const Job j = job_p6(t);
+            const JobB j = job_p6(t);
             float acc[2][4][4];
             // warps 0..5: tile pair (warp % 3) x batch half (warp / 3); tile pairs 0,1 = W_hh^T rows, pair 2 = W_ih^T rows
             const int pair = warp % 3, half = warp / 3;
             const bool act = warp < 6 && j.nkb > 0 && half * 32 < BI;
-            consume<2, 4>(ring, j, 2 * pair, 4 * half, pair == 2 ? 1 : 0, act, acc);
+            consume_tf32<2, 4>(ring, j, 2 * pair, 4 * half, pair == 2 ? 1 : 0, act, acc);
             if (act) {
                 const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
@@ -522,11 +317,11 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
 
         // ---------------- P9 (latent-group owners): dz of my (rows, group) = dx1_t . W_z, kept in smem for P1 of step t-1
         if (t > 0) {
-            const Job j = job_p9(t);
+            const JobB j = job_p9(t);
             float acc[1][1][4];
             // warps 0..3: class half (warp & 1) x row octet (warp >> 1)
             const bool act = warp < 4 && j.nkb > 0 && (warp & 1) * 16 < C && (warp >> 1) * 8 < b9_1 - b9_0;
-            consume<1, 1>(ring, j, warp & 1, warp >> 1, 0, act, acc);
+            consume_tf32<1, 1>(ring, j, warp & 1, warp >> 1, 0, act, acc);
             if (act) {
                 const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
@@ -550,24 +345,6 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
             }
         }
     }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// row-major [rows, K] matrix as a 2-D tensor map, boxes of 128 bytes x box_rows, 128-byte swizzle, zero OOB fill
-int bmap(pd_handle* h, CUtensorMap* tm, const void* base, long rows, int K, int box_rows, bool f16) {
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)K * (f16 ? 2 : 4)};
-    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                                                   (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "pd_rssm_unroll_bwd: cuTensorMapEncodeTiled failed (%d) for [%ld, %d]", (int)r, rows, K);
-    return PD_OK;
 }
 
 }  // namespace
@@ -604,17 +381,18 @@ extern "C" int pd_rssm_unroll_bwd(pd_handle* h, const pd_rssm_bwd_args* a_in, vo
     BwdMaps maps;
     memset(&maps, 0, sizeof(maps));
     const long rows = (long)a.T * a.BI;
-    int rc = bmap(h, &maps.wpmT, a.w_pmT16, a.Hd, Z, 16, true);
-    if (!rc) rc = bmap(h, &maps.wphT, a.w_phT16, a.D, a.Hd, 16, true);
-    if (!rc) rc = bmap(h, &maps.whhT, a.w_hhT16, a.D, D3, 16, true);
-    if (!rc) rc = bmap(h, &maps.wihT, a.w_ihT16, a.Hd, D3, 16, true);
-    if (!rc) rc = bmap(h, &maps.wzT, a.w_zT16, Z, a.Hd, 16, true);
-    if (!rc) rc = bmap(h, &maps.dpost, a.dpost, rows, Z, BROWS, false);
-    if (!rc) rc = bmap(h, &maps.dy2, a.dy2, rows, a.Hd, BROWS, false);
-    if (!rc) rc = bmap(h, &maps.dgh, a.dgh, rows, D3, BROWS, false);
-    if (!rc) rc = bmap(h, &maps.dgi, a.dgi, rows, D3, BROWS, false);
-    if (!rc) rc = bmap(h, &maps.dx1, a.dx1, rows, a.Hd, BROWS, false);
-    if (!rc) rc = bmap(h, &maps.dx1_16, a.dx1, rows, a.Hd, 16, false);
+    const char* who = "pd_rssm_unroll_bwd";
+    int rc = make_map(h, who, &maps.wpmT, a.w_pmT16, a.Hd, Z, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.wphT, a.w_phT16, a.D, a.Hd, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.whhT, a.w_hhT16, a.D, D3, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.wihT, a.w_ihT16, a.Hd, D3, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.wzT, a.w_zT16, Z, a.Hd, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.dpost, a.dpost, rows, Z, BROWS, false);
+    if (!rc) rc = make_map(h, who, &maps.dy2, a.dy2, rows, a.Hd, BROWS, false);
+    if (!rc) rc = make_map(h, who, &maps.dgh, a.dgh, rows, D3, BROWS, false);
+    if (!rc) rc = make_map(h, who, &maps.dgi, a.dgi, rows, D3, BROWS, false);
+    if (!rc) rc = make_map(h, who, &maps.dx1, a.dx1, rows, a.Hd, BROWS, false);
+    if (!rc) rc = make_map(h, who, &maps.dx1_16, a.dx1, rows, a.Hd, 16, false);
     if (rc) return rc;
     if (cudaMemsetAsync(a.ws_barrier, 0, 16 * sizeof(unsigned), s) != cudaSuccess)
         PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_bwd: memset failed");

@@ -1,0 +1,408 @@
+// pd_rssm_fwd3.cu — the posterior unroll of the RSSM as ONE persistent cooperative kernel (pd_rssm_unroll_fwd), third
+// generation: TMA-staged operands, producer warp, weight prefetch across grid barriers, k-split recurrent contraction.
+//
+// Reference semantics: pydreamer/models/rssm.py:21-78 (RSSMCore.forward time loop) and :125-153 (RSSMCell.forward:
+// z_mlp + a_mlp -> in_norm -> ELU -> GRUCell -> post_mlp_h + post_mlp_e -> post_norm -> ELU -> post_mlp ->
+// OneHotCategoricalStraightThrough sample).  Same contract (inputs, saved tensors, sampled indices) as the first-generation
+// kernel of round 1 (cp.async row staging, every CTA re-reading the whole activation operand; git history), which it replaces.
+//
+// Per timestep, five dependent phases separated by grid barriers (pd_k1_pipe.cuh):
+//   A   batch-row owners      : x1 = mask * gather(W_z^T, idx_{t-1}) + b_z + aa_t ; LayerNorm + ELU -> za          (z is one-hot)
+//   B   hidden-unit owners    : gi = za . W_ih^T (K = Hd) ; gh = sum of the k-slice partials of phase C ; GRU gates -> h'
+//   C   (row group, k slice)  : partials of gh_{t+1} = h' . W_hh^T and y2 = h' . W_ph^T over a quarter of K = D each:
+//                               every CTA stages 64 x D/4 of h' instead of 64 x D (r02 ncu of the first generation: the
+//                               re-read activation operand was 3x the weight stream); the partials are summed by their
+//                               consumers (unit owners in B, row owners in C'), which costs no extra barrier
+//   C'  batch-row owners      : y2 = sum of partials + b_ph + ea_t ; LayerNorm + ELU -> pin
+//   D   latent-group owners   : logits of group g for a quarter of the batch rows = pin . W_pm^T ; softmax ; argmax(p / q)
+// Weights are fp16, activations fp16 (za, h', pin: the same 10 mantissa bits as the TF32 chain), accumulation fp32.
+#include "pd_k1_pipe.cuh"
+
+namespace {
+using namespace k1;
+
+constexpr int MAXT = 14;                       // phase C: 3 gates x 4 tiles of W_hh rows + 2 tiles of W_ph rows
+typedef Ring<MAXT, 1> RingF;
+typedef Job<MAXT> JobF;
+constexpr int OFF_BAR = RingF::BYTES;
+constexpr int OFF_SH = OFF_BAR + 128;                       // 64 floats: block reductions
+constexpr int OFF_SIDX = OFF_SH + 256;                      // 64 ints: sampled classes of one row
+constexpr int OFF_HC = OFF_SIDX + 256;                      // [16][BROWS] floats: masked h of my units (input of the next step)
+constexpr int OFF_PART = OFF_HC + 16 * BROWS * 4;           // [2][1024] floats: phase A gather halves
+constexpr int OFF_LOG = OFF_PART + 2 * 1024 * 4;            // [16][32] floats: phase D logits of my rows
+constexpr int SMEM_BYTES = OFF_LOG + 16 * 32 * 4;
+constexpr int KSPLIT = 4;
+
+struct FwdMaps {
+    CUtensorMap wih, whh, wph, wpm;            // fp16 weights, box {64 halfs, 16 rows}
+    CUtensorMap za, h;                         // fp16 activations [BI, K], box {64 halfs, 64 rows}
+    CUtensorMap pin16;                         // fp16 [BI, Hd], box {64 halfs, 16 rows}
+};
+
+// LayerNorm + ELU of one row held as v[4] per consumer thread (features tid + 256 i); writes fp32 (fp16-representable) and
+// fp16 copies, mean / rstd.  Same formulas as ln_elu_fwd_kernel (pd_rowwise.cu).
+__device__ void ln_elu_row(float (&v)[4], int N, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           float* yrow, __half* y16row, float* mean_out, float* rstd_out, float* sh) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += (threadIdx.x + NCT * i < N) ? v[i] : 0.f;
+    const float mean = cons_sum(s, sh) / (float)N;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float d = (threadIdx.x + NCT * i < N) ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+    const float var = cons_sum(q, sh) / (float)N;
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + NCT * i;
+        if (c < N) {
+            const __half hv = __float2half_rn(pd_elu((v[i] - mean) * rstd * gamma[c] + beta[c]));
+            yrow[c] = __half2float(hv);
+            y16row[c] = hv;
+        }
+    }
+    if (threadIdx.x == 0) { *mean_out = mean; *rstd_out = rstd; }
+}
+
+__global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_fwd_args a, const __grid_constant__ FwdMaps maps,
+                                                                 const int KS) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* sh = (float*)(smem + OFF_SH);
+    int* sidx = (int*)(smem + OFF_SIDX);
+    float* hcs = (float*)(smem + OFF_HC);                   // hcs[r * BROWS + b]
+    float* part = (float*)(smem + OFF_PART);                // [2][Hd]
+    float* lgs = (float*)(smem + OFF_LOG);                  // lgs[rb * 32 + class]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool producer = warp == NCW;
+    const int P = gridDim.x, c = blockIdx.x;
+    const int T = a.T, BI = a.BI, D = a.D, Hd = a.Hd, G = a.G, C = a.C, Z = G * C, F = D + Z, D3 = 3 * D;
+    const int Bq = BI / a.I;                                // sequences (rows of aa / ea per timestep)
+    const __half* wzT = (const __half*)a.ws_wzT16;          // [Z][Hd], transposed z_mlp weight (written by the host)
+    __half* za16 = (__half*)a.ws_za16;
+    __half* h16 = (__half*)a.ws_h16;
+    __half* pin16 = (__half*)a.ws_pin16;
+
+    RingF ring;
+    ring.init(smem, (uint64_t*)(smem + OFF_BAR));
+
+    // ---- static ownership
+    const int u4_0 = (int)((long)c * D / P), u4_1 = (int)((long)(c + 1) * D / P), nu = u4_1 - u4_0;   // B: my hidden units
+    const int RG = P / KS, rg = c / KS, ks = c % KS;                                                    // C: row group x k slice
+    const bool inC = rg < RG;
+    const int u6_0 = (int)((long)rg * D / RG), u6_1 = inC ? (int)((long)(rg + 1) * D / RG) : u6_0;     // C: gh rows (units)
+    const int f6_0 = (int)((long)rg * Hd / RG), f6_1 = inC ? (int)((long)(rg + 1) * Hd / RG) : f6_0;   // C: y2 features
+    const int kslice = D / KS;
+    const int R = max(1, min(4, P / G));                                                                 // D: CTAs per group
+    const int RB = (BI + R - 1) / R;                                                                     // rows per such CTA
+    const bool inD = c < G * R;
+    const int g9 = c / R, sub9 = c % R, b9_0 = sub9 * RB, b9_1 = min(BI, b9_0 + RB);
+
+    for (int o = tid; o < nu * BI; o += NT) hcs[(o % nu) * BROWS + o / nu] = __ldcg(a.hin + (long)(o / nu) * D + u4_0 + o % nu);
+    __syncthreads();
+
+    auto job_b = [&]() {
+        JobF j; j.ntile = nu > 0 ? 3 : 0; j.nx = 1; j.xmap[0] = &maps.za; j.xmap[1] = &maps.za; j.xrow0 = 0; j.xrows = BROWS; j.xf16 = 1;
+        j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
+        for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wih; j.row0[i] = (i % 3) * D + u4_0; }
+        return j;
+    };
+    auto job_c = [&]() {
+        JobF j; j.ntile = inC ? MAXT : 0; j.nx = 1; j.xmap[0] = &maps.h; j.xmap[1] = &maps.h; j.xrow0 = 0; j.xrows = BROWS; j.xf16 = 1;
+        j.kcol0 = ks * kslice; j.nkb = j.ntile ? (kslice + KB - 1) / KB : 0; j.x2_from = 1 << 30;
+        for (int i = 0; i < 12; ++i) { j.wmap[i] = &maps.whh; j.row0[i] = (i / 4) * D + u6_0 + 16 * (i % 4); }   // tile = gate * 4 + i
+        for (int i = 0; i < 2; ++i) { j.wmap[12 + i] = &maps.wph; j.row0[12 + i] = f6_0 + 16 * i; }
+        return j;
+    };
+    auto job_d = [&]() {
+        JobF j; j.ntile = inD ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = &maps.pin16; j.xmap[1] = &maps.pin16; j.xrow0 = b9_0; j.xrows = 16;
+        j.xf16 = 1; j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
+        for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wpm; j.row0[i] = g9 * C + 16 * i; }
+        return j;
+    };
+
+    // ================================================= producer warp =================================================
+    if (producer) {
+        if (lane == 0) {
+            unsigned epoch = 0;
+            // prologue: barrier 1 publishes h16 = fp16(h_0); then the phase-C job computes gh_0 partials; barrier 2
+            { const JobF j = job_c(); if (j.nkb) produce(ring, j, a.ws_barrier, 1); }
+            epoch = 2;
+            for (int t = 0; t < T; ++t) {
+                // barriers of a step: after A (1), after B (2), after C (3), after C' (4), after D (5, not on the last step)
+                { const JobF j = job_b(); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 1); }
+                { const JobF j = job_c(); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 2); }
+                { const JobF j = job_d(); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 4); }
+                epoch += 5;
+            }
+        }
+        return;
+    }
+
+    // ================================================= consumer warps =================================================
+    unsigned epoch = 0;
+    // phase C: partial products of my rows over my k slice -> global (gh partials only when want_gh, y2 partials when want_y2)
+    auto phase_c = [&](bool want_gh, bool want_y2) {
+        const JobF j = job_c();
+        float acc[4][4][4];
+        // 8 warps = 4 tile groups (gate r, gate u, gate n, W_ph rows) x 2 batch halves
+        const int grp = warp & 3, half = warp >> 2;
+        const bool act = j.nkb > 0 && half * 32 < BI;
+        consume_f16<4, 4>(ring, j, 4 * grp, 4 * half, act, acc);
+        if (!act) return;
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = 16 * i + g + 8 * (e >> 1), b = (4 * half + jn) * 8 + 2 * tq + (e & 1);
+                    if (b >= BI) continue;
+                    if (grp < 3) {
+                        const int u = u6_0 + r;
+                        if (want_gh && u < u6_1) a.ws_ghpart[((long)ks * BI + b) * D3 + (long)grp * D + u] = acc[i][jn][e];
+                    } else {
+                        const int f = f6_0 + r;
+                        if (want_y2 && i < 2 && f < f6_1) a.ws_y2part[((long)ks * BI + b) * Hd + f] = acc[i][jn][e];
+                    }
+                }
+    };
+
+    // ---- prologue: fp16 h_0 for the TMA reads of the first recurrent product
+    for (long i = (long)c * NCT + tid; i < (long)BI * D; i += (long)P * NCT) h16[i] = __float2half_rn(__ldcg(a.hin + i));
+    grid_barrier(a.ws_barrier, epoch);                                          // (p1)
+    phase_c(true, false);                                                       // gh_0 = h_0 . W_hh^T (raw; bias and mask at use)
+    grid_barrier(a.ws_barrier, epoch);                                          // (p2)
+
+    for (int t = 0; t < T; ++t) {
+        // ---- phase A (CTA b < BI): x1 = mask * gather(WzT, idx_{t-1}) + b_z + aa_t ; LayerNorm + ELU -> za
+        if (c < BI) {
+            const int b = c;
+            const long row = (long)t * BI + b;
+            float v[4];
+            if (t > 0) {
+                const float m = a.mask[row];
+                for (int gg = tid; gg < G; gg += NCT) sidx[gg] = __ldcg(a.idx + ((long)(t - 1) * BI + b) * G + gg);
+                float pa[4];                                              // bias + action term, in flight during the gather
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int f = tid + NCT * i;
+                    pa[i] = f < Hd ? a.b_z[f] + a.aa[((long)t * Bq + b / a.I) * Hd + f] : 0.f;
+                }
+                cons_sync();
+                {   // gather-sum of G rows of WzT: thread = (8 features, half of the groups), 16-byte loads, all independent
+                    const int fg = tid & 127, gh = tid >> 7;
+                    if (fg * 8 < Hd) {
+                        float s8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) s8[e] = 0.f;
+                        const int g0 = gh * ((G + 1) / 2), g1 = min(G, g0 + (G + 1) / 2);
+#pragma unroll 4
+                        for (int gg = g0; gg < g1; ++gg) {
+                            const uint4 w = *(const uint4*)(wzT + (long)(gg * C + sidx[gg]) * Hd + fg * 8);
+                            const __half2* h2 = (const __half2*)&w;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f2 = __half22float2(h2[e]);
+                                s8[2 * e] += f2.x; s8[2 * e + 1] += f2.y;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) part[gh * Hd + fg * 8 + e] = s8[e];
+                    }
+                }
+                cons_sync();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int f = tid + NCT * i;
+                    v[i] = 0.f;
+                    if (f < Hd) {
+                        v[i] = m * (part[f] + part[Hd + f]) + pa[i];
+                        a.x1[row * Hd + f] = v[i];
+                    }
+                }
+                for (int jz = tid; jz < Z; jz += NCT) a.zin[row * Z + jz] = (sidx[jz / C] == jz % C) ? m : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int f = tid + NCT * i;
+                    v[i] = f < Hd ? __ldcg(a.x1 + row * Hd + f) : 0.f;
+                }
+            }
+            ln_elu_row(v, Hd, a.ln1_g, a.ln1_b, a.eps, a.za + row * Hd, za16 + (long)b * Hd, a.m1 + row, a.r1 + row, sh);
+        }
+        grid_barrier(a.ws_barrier, epoch);                                      // (1) za complete
+
+        // ---- phase B (hidden-unit owners): gi = za . W_ih^T, GRU gate math, h' -> feat / hin[t+1] / h16
+        {
+            const JobF j = job_b();
+            float acc[3][2][4];
+            const bool act = warp < 4 && j.nkb > 0 && warp * 16 < BI;          // warp = pair of n8-tiles of batch rows
+            consume_f16<3, 2>(ring, j, 0, 2 * warp, act, acc);
+            if (act) {
+                const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+                for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = g + 8 * (e >> 1), b = (2 * warp + jn) * 8 + 2 * tq + (e & 1), u = u4_0 + r;
+                        if (r >= nu || b >= BI) continue;
+                        const long row = (long)t * BI + b;
+                        const float m = t > 0 ? a.mask[row] : 1.f;              // h_0 arrives already masked
+                        const float mn = t + 1 < T ? a.mask[row + BI] : 0.f;
+                        float gh0 = 0.f, gh1 = 0.f, gh2 = 0.f;
+                        for (int k = 0; k < KS; ++k) {
+                            const float* gp = a.ws_ghpart + ((long)k * BI + b) * D3 + u;
+                            gh0 += __ldcg(gp); gh1 += __ldcg(gp + D); gh2 += __ldcg(gp + 2 * D);
+                        }
+                        const float ghr = m * gh0 + a.b_hh[u];
+                        const float ghu = m * gh1 + a.b_hh[D + u];
+                        const float ghn = m * gh2 + a.b_hh[2 * D + u];
+                        const float rg_ = pd_sigmoid(acc[0][jn][e] + a.b_ih[u] + ghr);
+                        const float ug_ = pd_sigmoid(acc[1][jn][e] + a.b_ih[D + u] + ghu);
+                        const float ng_ = tanhf(acc[2][jn][e] + a.b_ih[2 * D + u] + rg_ * ghn);
+                        const float hp = hcs[r * BROWS + b];
+                        const __half hh = __float2half_rn((1.f - ug_) * ng_ + ug_ * hp);
+                        const float hn = __half2float(hh);
+                        a.feat[row * F + u] = hn;
+                        h16[(long)b * D + u] = hh;
+                        hcs[r * BROWS + b] = hn * mn;
+                        if (t + 1 < T) a.hin[(row + BI) * D + u] = hn * mn;
+                        float* gt = a.gates + row * 4 * D;
+                        gt[u] = rg_; gt[D + u] = ug_; gt[2 * D + u] = ng_; gt[3 * D + u] = ghn;
+                    }
+            }
+        }
+        grid_barrier(a.ws_barrier, epoch);                                      // (2) h' complete
+
+        // ---- phase C: partials of y2 = h' . W_ph^T and of gh_{t+1} = h' . W_hh^T
+        phase_c(t + 1 < T, true);
+        grid_barrier(a.ws_barrier, epoch);                                      // (3) partials complete
+
+        // ---- phase C' (CTA b < BI): y2 = partial sums + b_ph + ea_t ; LayerNorm + ELU -> pin
+        if (c < BI) {
+            const int b = c;
+            const long row = (long)t * BI + b;
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int f = tid + NCT * i;
+                v[i] = 0.f;
+                if (f < Hd) {
+                    float s = a.b_ph[f] + (a.ea ? a.ea[((long)t * Bq + b / a.I) * Hd + f] : 0.f);
+                    for (int k = 0; k < KS; ++k) s += __ldcg(a.ws_y2part + ((long)k * BI + b) * Hd + f);
+                    v[i] = s;
+                    a.y2[row * Hd + f] = s;
+                }
+            }
+            ln_elu_row(v, Hd, a.ln2_g, a.ln2_b, a.eps, a.pin + row * Hd, pin16 + (long)b * Hd, a.m2 + row, a.r2 + row, sh);
+        }
+        grid_barrier(a.ws_barrier, epoch);                                      // (4) pin complete
+
+        // ---- phase D (latent-group owners): logits of group g for my rows, softmax, argmax(p / q) -> post, idx, z
+        if (inD) {
+            const JobF j = job_d();
+            float acc[1][2][4];
+            const bool act = warp < 2 && warp * 16 < C;                         // warp = 16 classes of the group, both n8-tiles of my rows
+            consume_f16<1, 2>(ring, j, warp, 0, act, acc);
+            if (act) {
+                const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+                for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int cls = 16 * warp + g + 8 * (e >> 1), rb = jn * 8 + 2 * tq + (e & 1);
+                        if (cls < C) lgs[rb * 32 + cls] = acc[0][jn][e];
+                    }
+            }
+            cons_sync();
+            const float pbias = lane < C ? a.b_pm[g9 * C + lane] : 0.f;
+            for (int rb = warp; rb < b9_1 - b9_0; rb += NCW) {
+                const int b = b9_0 + rb;
+                const long row = (long)t * BI + b;
+                const bool valid = lane < C;
+                const float q = valid ? a.noise[row * Z + g9 * C + lane] : 1.f;
+                float l = 0.f;
+                if (valid) {
+                    l = lgs[rb * 32 + lane] + pbias;
+                    a.post[row * Z + g9 * C + lane] = l;
+                }
+                // same arithmetic as cat_sample_kernel (pd_rowwise.cu): logits - logsumexp, softmax, argmax(p / q)
+                const float mx = pd_warp_max(valid ? l : -INFINITY);
+                const float e = valid ? expf(l - mx) : 0.f;
+                const float lse = mx + logf(pd_warp_sum(e));
+                const float ln = valid ? l - lse : -INFINITY;
+                const float mx2 = pd_warp_max(ln);
+                const float e2 = valid ? expf(ln - mx2) : 0.f;
+                const float p = e2 / pd_warp_sum(e2);
+                float val = valid ? p / q : -INFINITY;
+                int k = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+                    const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+                    if (ov > val || (ov == val && ok < k)) { val = ov; k = ok; }
+                }
+                if (valid) a.feat[row * F + D + g9 * C + lane] = (lane == k) ? 1.f : 0.f;
+                if (lane == 0) a.idx[row * G + g9] = k;
+            }
+        }
+        if (t + 1 < T) grid_barrier(a.ws_barrier, epoch);                       // (5) idx_t complete
+        else epoch += 1;
+    }
+}
+
+}  // namespace
+
+extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream) {
+    if (!h || !a) return PD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    PdDeviceGuard guard(h);
+    constexpr size_t SMEM_REQ = (size_t)SMEM_BYTES + 1024;
+    if (!h->k1_configured) {
+        if (cudaFuncSetAttribute(rssm_unroll_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_REQ) != cudaSuccess)
+            PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: cannot reserve %d bytes of shared memory", (int)SMEM_REQ);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rssm_unroll_fwd3_kernel, NT, SMEM_REQ);
+        h->k1_ctas = per_sm > 0 ? h->num_sms : 0;             // one CTA per SM
+        h->k1_configured = 1;
+    }
+    const int P = h->k1_ctas;
+    PD_REQUIRE(h, P > 0, "pd_rssm_unroll_fwd: kernel does not fit an SM");
+    const int Z = a->G * a->C;
+    const int KS = (a->D % (KSPLIT * KB) == 0 && P >= KSPLIT) ? KSPLIT : 1;
+    const int RG = P / KS;
+    const int R = P / a->G < 4 ? (P / a->G < 1 ? 1 : P / a->G) : 4;
+    const bool ok = a->T >= 1 && a->BI >= 1 && a->BI <= BROWS && a->BI <= P && a->I >= 1 && a->BI % a->I == 0 &&
+                    a->Hd <= 4 * NCT && a->Hd % 8 == 0 && a->D % 8 == 0 && a->C >= 1 && a->C <= 32 && a->G >= 1 && a->G <= P &&
+                    (a->BI + R - 1) / R <= 16 && (a->D + P - 1) / P <= 16 && (a->D + RG - 1) / RG <= 64 &&
+                    (a->Hd + RG - 1) / RG <= 32 && Z >= 1 && a->ws_ghpart && a->ws_y2part && a->ws_wzT16;
+    if (!ok)
+        PD_FAIL(h, PD_ERR_UNSUPPORTED, "pd_rssm_unroll_fwd: shape T=%d BI=%d D=%d Hd=%d G=%d C=%d outside the kernel's limits",
+                a->T, a->BI, a->D, a->Hd, a->G, a->C);
+    FwdMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const char* who = "pd_rssm_unroll_fwd";
+    int rc = make_map(h, who, &maps.wih, a->w_ih16, 3L * a->D, a->Hd, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.whh, a->w_hh16, 3L * a->D, a->D, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.wph, a->w_ph16, a->Hd, a->D, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.wpm, a->w_pm16, Z, a->Hd, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.za, a->ws_za16, a->BI, a->Hd, BROWS, true);
+    if (!rc) rc = make_map(h, who, &maps.h, a->ws_h16, a->BI, a->D, BROWS, true);
+    if (!rc) rc = make_map(h, who, &maps.pin16, a->ws_pin16, a->BI, a->Hd, 16, true);
+    if (rc) return rc;
+    if (cudaMemsetAsync(a->ws_barrier, 0, 16 * sizeof(unsigned), s) != cudaSuccess)
+        PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: memset failed");
+    pd_rssm_fwd_args args = *a;
+    int ksv = KS;
+    void* kargs[] = {(void*)&args, (void*)&maps, (void*)&ksv};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)rssm_unroll_fwd3_kernel, dim3(P), dim3(NT), kargs, SMEM_REQ, s);
+    if (e != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: %s", cudaGetErrorString(e));
+    PD_CHECK_LAUNCH(h, "pd_rssm_unroll_fwd");
+    return PD_OK;
+}

@@ -552,6 +552,10 @@ class Dreamer(nn.Module):
             sh = self._buf(f"decw{li}", kh, kw, co, ci)
             ops.permute4(self._w(w), sh, (2, 3, 1, 0))
             self._decw.append(sh.view(kh * kw * co, ci))
+        if self.persistent_rssm:      # z_mlp^T [Z, Hd] fp16: a one-hot latent selects rows (persistent unroll, phase A)
+            wz = self.wm.core.cell.z_mlp.weight
+            self._k1_wzT = self._buf("k1.wzT", wz.shape[1], wz.shape[0], dtype=torch.float16)
+            ops.transpose_to_half(self._raw(wz), self._k1_wzT)
         if self.persistent_bptt:      # transposed fp16 copies: operands of the persistent BPTT kernel (pd_rssm_unroll_bwd)
             cell = self.wm.core.cell
             gru = cell.gru.layers[0]
@@ -780,7 +784,7 @@ class Dreamer(nn.Module):
     # written after the round's GPU budget was spent, so it is off until it has been run and measured on a B200.
     direct_conv1 = os.environ.get("PD_B200_DIRECT_CONV1", "0") != "0"
 
-    # The posterior unroll runs as ONE cooperative kernel (csrc/pd_rssm_persistent.cu) when the shape fits its limits
+    # The posterior unroll runs as ONE cooperative kernel (csrc/pd_rssm_fwd3.cu) when the shape fits its limits
     # (B*I <= 64 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
     persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "1") != "0"
 
@@ -810,8 +814,12 @@ class Dreamer(nn.Module):
         if not (self.persistent_rssm and self.fp16_forward and self._dp_allows() and (on_gpu or self.ops.is_reference)):
             return False
         P = torch.cuda.get_device_properties(self._arena.device).multi_processor_count if on_gpu else 148
-        return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and
-                d.G <= min(64, P) and -(-d.D // P) <= 16 and -(-d.Hd // P) <= 16)
+        ks = 4 if d.D % 256 == 0 and P >= 4 else 1
+        R = max(1, min(4, P // d.G))
+        cd = lambda a_, b_: -(-a_ // b_)
+        return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and d.G <= P and
+                cd(BI, R) <= 16 and cd(d.D, P) <= 16 and cd(d.D, P // ks) <= 64 and cd(d.Hd, P // ks) <= 32 and
+                getattr(self, "_k1_wzT", None) is not None)
 
     def _ov(self, bit):
         # (the eager phase timer of bench.py needs one stream)
@@ -932,7 +940,7 @@ class Dreamer(nn.Module):
         W = self._w
         if self._persistent_rssm_ok(BI):
             try:
-                # one cooperative kernel for all T steps (csrc/pd_rssm_persistent.cu); step 0's pre-norm input is formed
+                # one cooperative kernel for all T steps (csrc/pd_rssm_fwd3.cu); step 0's pre-norm input is formed
                 # here because the incoming z need not be one-hot
                 Wh, h16 = self._wh, torch.float16
                 ops.gemm(zin[0], W(cell.z_mlp.weight), x1[0], bias=self._raw(cell.z_mlp.bias), res=aa[:B], r_div=I)
@@ -946,9 +954,10 @@ class Dreamer(nn.Module):
                     b_ph=self._raw(ph.bias), ln2_g=self._raw(pn.weight), ln2_b=self._raw(pn.bias), b_pm=self._raw(pm.bias),
                     aa=aa, ea=None if open_loop else ea, mask=mask, noise=noise_post, x1=x1, za=za, m1=m1, r1=r1,
                     gates=gates, feat=feat, hin=hin, zin=zin, y2=y2, pin=pin, m2=m2, r2=r2, post=post, idx=idx,
-                    ws_wzT16=b("k1.wzT", d.Z, d.Hd, dtype=h16), ws_za16=b("k1.za16", BI, d.Hd, dtype=h16),
+                    ws_wzT16=self._k1_wzT, ws_za16=b("k1.za16", BI, d.Hd, dtype=h16),
                     ws_h16=b("k1.h16", BI, d.D, dtype=h16), ws_pin16=b("k1.pin16", BI, d.Hd, dtype=h16),
-                    ws_barrier=b("k1.bar", 16, dtype=torch.int32))
+                    ws_barrier=b("k1.bar", 16, dtype=torch.int32), ws_ghpart=b("k1.ghpart", 4, BI, 3 * d.D),
+                    ws_y2part=b("k1.y2part", 4, BI, d.Hd))
                 out_state = (feat[T - 1, :, :d.D].clone(), feat[T - 1, :, d.D:].clone())
                 return img, post, idx, out_state
             except RuntimeError as e:        # e.g. cooperative launch refused (SMs reserved by MPS / green contexts)

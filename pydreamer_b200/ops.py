@@ -39,7 +39,7 @@ class RssmFwdArgs(ctypes.Structure):
     _PTRS1 = ("w_z16", "w_ih16", "w_hh16", "w_ph16", "w_pm16", "b_z", "ln1_g", "ln1_b", "b_ih", "b_hh", "b_ph",
               "ln2_g", "ln2_b", "b_pm")
     _PTRS2 = ("aa", "ea", "mask", "noise", "x1", "za", "m1", "r1", "gates", "feat", "hin", "zin", "y2", "pin", "m2",
-              "r2", "post", "idx", "ws_wzT16", "ws_za16", "ws_h16", "ws_pin16", "ws_barrier")
+              "r2", "post", "idx", "ws_wzT16", "ws_za16", "ws_h16", "ws_pin16", "ws_barrier", "ws_ghpart", "ws_y2part")
     _fields_ = ([(n, ctypes.c_int) for n in _INTS] + [(n, ctypes.c_void_p) for n in _PTRS1] +
                 [("eps", ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS2])
 
@@ -207,10 +207,7 @@ class NativeOps:
                 assert v.is_contiguous(), n
                 setattr(a, n, v.data_ptr())
         assert not t, f"unknown fields {sorted(t)}"
-        if os.environ.get("PD_B200_K1_STAGING", "") == "tma":     # work-in-progress kernel (csrc/pd_rssm_persistent_v2.cu)
-            self._ck(self.lib.pd_rssm_unroll_fwd_v2(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd_v2")
-        else:
-            self._ck(self.lib.pd_rssm_unroll_fwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd")
+        self._ck(self.lib.pd_rssm_unroll_fwd(self.h, ctypes.byref(a), self._s()), "pd_rssm_unroll_fwd")
 
     def rssm_unroll_bwd(self, dims, kl_weight, round_out=True, **t):
         """Persistent BPTT of the posterior unroll (pd_rssm_unroll_bwd).  dims = dict(T, BI, D, Hd, G, C); every pointer

@@ -81,9 +81,9 @@ def test_sass_of_the_persistent_bptt_kernel():
 
 
 def test_sass_of_the_persistent_rssm_kernel():
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "rssm_unroll_fwd_kernel", _native.LIB_PATH],
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "rssm_unroll_fwd3_kernel", _native.LIB_PATH],
                           capture_output=True, text=True).stdout
     if "HMMA" not in sass:                       # older cuobjdump: -fun wants the mangled name; fall back to the whole file
         sass = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
     assert "HMMA.16816.F32" in sass              # mma.sync.m16n8k16 f16 -> f32
-    assert "LDGSTS" in sass and "LDSM" in sass   # cp.async staging, ldmatrix operand reads
+    assert "UTMALDG.2D" in sass and "LDSM" in sass   # TMA tile staging, ldmatrix operand reads

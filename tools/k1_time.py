@@ -1,5 +1,4 @@
-"""Times pd_rssm_unroll_fwd (persistent posterior unroll, Atari shape): CUDA events around the call and the kernel's own
-per-phase nanosecond counters (ws_barrier words 2..15: prologue, gh0, A gather+LN, B gi+GRU, C y2+gh, C' LN, D logits+sample)."""
+"""Times pd_rssm_unroll_fwd (persistent posterior unroll, Atari shape by default): CUDA events around the call."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +6,7 @@ from pydreamer_b200.config import make_conf
 from pydreamer_b200.dreamer import Dreamer
 from pydreamer_b200.replay import synthetic_batch
 
-conf = make_conf("atari", device="cuda:0")
+conf = make_conf(sys.argv[1] if len(sys.argv) > 1 else "atari", device="cuda:0")
 obs = synthetic_batch(conf, seed=1, device="cuda:0")
 model = Dreamer(conf).to("cuda:0")
 model.persistent_rssm = True
@@ -25,10 +24,4 @@ with torch.no_grad():
     for _ in range(3):
         model.training_step(obs, state)
 torch.cuda.synchronize()
-bar = model._buf("k1.bar", 16, dtype=torch.int32)
-ns = bar[2:16].view(torch.int64).tolist()
-names = ["prologue", "gh0", "A_gather_ln", "B_gi_gru", "C_y2_gh", "Cp_ln", "D_logits_sample"]
-T = conf.batch_length
-print(json.dumps(dict(kernel_ms=[round(a.elapsed_time(b), 3) for a, b in times],
-                      phase_us_per_step={n: round(v / 1000 / (1 if i < 2 else T), 2) for i, (n, v) in enumerate(zip(names, ns))},
-                      total_ms_from_phases=round(sum(ns) / 1e6, 3))))
+print(json.dumps(dict(kernel_ms=[round(a.elapsed_time(b), 3) for a, b in times])))
