@@ -109,6 +109,26 @@ __device__ __forceinline__ void producer_wait_barrier(const unsigned* ctr, unsig
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// Diagnostic: CTA 0 accumulates the nanoseconds between consecutive laps per phase slot into ws_barrier[2 + 2 * slot]
+// (7 uint64 counters, read by tools/k1_time.py / k1b_time.py); one clock read per phase, no effect on the result.
+struct PhaseClock {
+    unsigned long long last;
+    unsigned long long* acc;
+    __device__ __forceinline__ static unsigned long long now() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ void start(unsigned* ws) { acc = (unsigned long long*)(ws + 2); last = now(); }
+    __device__ void lap(int slot) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long t = now();
+            acc[slot] += t - last;
+            last = t;
+        }
+    }
+};
+
 // Stage layout: MAXT weight tiles, then XB activation boxes (X_BOX bytes apart).
 template <int MAXT, int XB>
 struct Ring {                       // both sides count stages identically: slot = n % NSTAGE, parity = (n / NSTAGE) & 1

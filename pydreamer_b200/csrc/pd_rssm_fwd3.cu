@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
 
     // ================================================= consumer warps =================================================
     unsigned epoch = 0;
+    PhaseClock clk;
+    clk.start(a.ws_barrier);
     // phase C: partial products of my rows over my k slice -> global (gh partials only when want_gh, y2 partials when want_y2)
     auto phase_c = [&](bool want_gh, bool want_y2) {
         const JobF j = job_c();
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
     grid_barrier(a.ws_barrier, epoch);                                          // (p1)
     phase_c(true, false);                                                       // gh_0 = h_0 . W_hh^T (raw; bias and mask at use)
     grid_barrier(a.ws_barrier, epoch);                                          // (p2)
+    clk.lap(0);
 
     for (int t = 0; t < T; ++t) {
         // ---- phase A (CTA b < BI): x1 = mask * gather(WzT, idx_{t-1}) + b_z + aa_t ; LayerNorm + ELU -> za
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
             ln_elu_row(v, Hd, a.ln1_g, a.ln1_b, a.eps, a.za + row * Hd, za16 + (long)b * Hd, a.m1 + row, a.r1 + row, sh);
         }
         grid_barrier(a.ws_barrier, epoch);                                      // (1) za complete
+        clk.lap(1);
 
         // ---- phase B (hidden-unit owners): gi = za . W_ih^T, GRU gate math, h' -> feat / hin[t+1] / h16
         {
@@ -279,10 +283,12 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
             }
         }
         grid_barrier(a.ws_barrier, epoch);                                      // (2) h' complete
+        clk.lap(2);
 
         // ---- phase C: partials of y2 = h' . W_ph^T and of gh_{t+1} = h' . W_hh^T
         phase_c(t + 1 < T, true);
         grid_barrier(a.ws_barrier, epoch);                                      // (3) partials complete
+        clk.lap(3);
 
         // ---- phase C' (CTA b < BI): y2 = partial sums + b_ph + ea_t ; LayerNorm + ELU -> pin
         if (c < BI) {
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
             ln_elu_row(v, Hd, a.ln2_g, a.ln2_b, a.eps, a.pin + row * Hd, pin16 + (long)b * Hd, a.m2 + row, a.r2 + row, sh);
         }
         grid_barrier(a.ws_barrier, epoch);                                      // (4) pin complete
+        clk.lap(4);
 
         // ---- phase D (latent-group owners): logits of group g for my rows, softmax, argmax(p / q) -> post, idx, z
         if (inD) {
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
             }
         }
         if (t + 1 < T) grid_barrier(a.ws_barrier, epoch);                       // (5) idx_t complete
-        else epoch += 1;
+        clk.lap(5);
     }
 }
 

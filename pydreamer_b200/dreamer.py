@@ -788,9 +788,11 @@ class Dreamer(nn.Module):
     # (B*I <= 64 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
     persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "1") != "0"
 
-    # BPTT through the posterior unroll as ONE cooperative kernel (csrc/pd_rssm_bptt.cu); PD_B200_PERSISTENT_BPTT=0 selects the
-    # chain of ~12 launches per timestep instead.
-    persistent_bptt = os.environ.get("PD_B200_PERSISTENT_BPTT", "1") != "0"
+    # BPTT through the posterior unroll as ONE cooperative kernel (csrc/pd_rssm_bptt.cu): opt-in with PD_B200_PERSISTENT_BPTT=1.
+    # Default is the chain of ~12 launches per timestep: standalone the two take the same 4 ms, but the chain's latency-bound
+    # launches share the SMs with the concurrent imagination branch while a cooperative kernel owns all of them for its whole
+    # duration (measured on B200, r02: 27.7 ms/step with the chain, 30.6 ms with the kernel).
+    persistent_bptt = os.environ.get("PD_B200_PERSISTENT_BPTT", "0") != "0"
 
     def _persistent_bptt_ok(self, BI):
         d = self.d

@@ -259,7 +259,7 @@ def test_persistent_bptt_kernel_matches_the_per_step_chain_at_full_size(preset, 
     for mode in (False, True):
         model = Dreamer(conf).to(DEV)
         model.load_state_dict(seeded_state_dict(model.state_dict(), 11))
-        model.persistent_bptt = mode
+        model.persistent_bptt = mode                           # opt-in switch (PD_B200_PERSISTENT_BPTT)
         losses, *_ = model.training_step(obs, state, noise=noise)
         for l in losses:
             l.backward()

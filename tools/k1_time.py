@@ -24,4 +24,10 @@ with torch.no_grad():
     for _ in range(3):
         model.training_step(obs, state)
 torch.cuda.synchronize()
-print(json.dumps(dict(kernel_ms=[round(a.elapsed_time(b), 3) for a, b in times])))
+bar = model._buf("k1.bar", 16, dtype=torch.int32)
+ns = bar[2:16].view(torch.int64).tolist()
+names = ["prologue+gh0", "A_gather_ln", "B_gi_gru", "C_hh_ph_partials", "Cp_ln", "D_logits_sample"]
+T = conf.batch_length
+print(json.dumps(dict(kernel_ms=[round(a.elapsed_time(b), 3) for a, b in times],
+                      phase_us_per_step={n: round(v / 1000 / (1 if i == 0 else T), 2) for i, (n, v) in enumerate(zip(names, ns))},
+                      total_ms_from_phases=round(sum(ns[:6]) / 1e6, 3))))

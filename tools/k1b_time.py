@@ -47,5 +47,10 @@ for mode in (True, False):
         step()
     torch.cuda.synchronize()
     out["persistent_ms" if mode else "chain_ms"] = [round(a.elapsed_time(b), 3) for a, b in times]
+    if mode:
+        T = conf.batch_length
+        ns = model._buf("k1b.bar", 16, dtype=torch.int32)[2:16].view(torch.int64).tolist()
+        names = ["P1_dpost", "P2_dpin", "P3_ln2_bwd", "P4_dh_gru_bwd", "P67_dhin_dza", "P8_ln1_bwd", "P9_dz"]
+        out["phase_us_per_step"] = {n: round(v / 1000 / T, 2) for n, v in zip(names, ns)}
     del model
 print(json.dumps(out))
