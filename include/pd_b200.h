@@ -161,7 +161,7 @@ typedef struct pd_rssm_fwd_args {
     void *ws_wzT16;                            /* in: fp16 [Z,Hd] = z_mlp.weight^T (pd_transpose_to_half) */
     void *ws_za16, *ws_h16, *ws_pin16;         /* workspace fp16 [BI,Hd] [BI,D] [BI,Hd] */
     unsigned int *ws_barrier;                  /* workspace, 16 words, 8-byte aligned, cleared by the call: [0] barrier counter */
-    float *ws_ghpart, *ws_y2part;              /* workspace [4,BI,3D] [4,BI,Hd]: k-slice partial sums of the recurrent products */
+    float *ws_ghpart, *ws_y2part;              /* workspace 4*BI*3D and 4*BI*Hd floats: k-slice partial sums of the recurrent products */
 } pd_rssm_fwd_args;
 int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void* stream);
 

@@ -16,12 +16,17 @@
 //   C'  batch-row owners      : y2 = sum of partials + b_ph + ea_t ; LayerNorm + ELU -> pin
 //   D   latent-group owners   : logits of group g for a quarter of the batch rows = pin . W_pm^T ; softmax ; argmax(p / q)
 // Weights are fp16, activations fp16 (za, h', pin: the same 10 mantissa bits as the TF32 chain), accumulation fp32.
+// The two wide contractions (B, C) run on the 5th-generation tensor cores: tcgen05.mma.kind::f16, M = 128 weight rows (eight
+// 16-row TMA boxes form one UMMA A tile), N = 64 batch rows, accumulators in TMEM, read back with tcgen05.ld for the
+// epilogues (r02 phase clocks of the mma.sync version: phase C spent 8.6 of its 11.4 us issuing legacy HMMA).  The small
+// logits contraction of phase D (32 rows x 16 batch rows) stays on mma.sync.
 #include "pd_k1_pipe.cuh"
 
 namespace {
 using namespace k1;
 
-constexpr int MAXT = 14;                       // phase C: 3 gates x 4 tiles of W_hh rows + 2 tiles of W_ph rows
+constexpr int MAXT = 16;                       // phase C: 3 gates x 4 tiles of W_hh rows + 2 tiles of W_ph rows = 14 of the
+                                               // 16 box slots of two 128-row UMMA tiles
 typedef Ring<MAXT, 1> RingF;
 typedef Job<MAXT> JobF;
 constexpr int OFF_BAR = RingF::BYTES;
@@ -30,7 +35,10 @@ constexpr int OFF_SIDX = OFF_SH + 256;                      // 64 ints: sampled 
 constexpr int OFF_HC = OFF_SIDX + 256;                      // [16][BROWS] floats: masked h of my units (input of the next step)
 constexpr int OFF_PART = OFF_HC + 16 * BROWS * 4;           // [2][1024] floats: phase A gather halves
 constexpr int OFF_LOG = OFF_PART + 2 * 1024 * 4;            // [16][32] floats: phase D logits of my rows
-constexpr int SMEM_BYTES = OFF_LOG + 16 * 32 * 4;
+constexpr int OFF_GI = OFF_LOG + 16 * 32 * 4;               // [48][65] floats: phase B gi of my units (from TMEM, for the gate math)
+constexpr int OFF_TM = OFF_GI + 48 * 65 * 4;                // accumulator-ready mbarrier (8 B) + TMEM base address (4 B)
+constexpr int SMEM_BYTES = OFF_TM + 64;
+constexpr int TMEM_COLS = 128;                              // two UMMA tiles x 64 batch columns
 constexpr int KSPLIT = 4;
 
 struct FwdMaps {
@@ -76,11 +84,14 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
     float* hcs = (float*)(smem + OFF_HC);                   // hcs[r * BROWS + b]
     float* part = (float*)(smem + OFF_PART);                // [2][Hd]
     float* lgs = (float*)(smem + OFF_LOG);                  // lgs[rb * 32 + class]
+    float* gis = (float*)(smem + OFF_GI);                   // gis[(gate * 16 + r) * 65 + b]
+    uint64_t* accbar = (uint64_t*)(smem + OFF_TM);
+    uint32_t* tmem_slot = (uint32_t*)(smem + OFF_TM + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool producer = warp == NCW;
     const int P = gridDim.x, c = blockIdx.x;
-    const int T = a.T, BI = a.BI, D = a.D, Hd = a.Hd, G = a.G, C = a.C, Z = G * C, F = D + Z, D3 = 3 * D;
+    const int T = a.T, BI = a.BI, D = a.D, Hd = a.Hd, G = a.G, C = a.C, Z = G * C, F = D + Z;
     const int Bq = BI / a.I;                                // sequences (rows of aa / ea per timestep)
     const __half* wzT = (const __half*)a.ws_wzT16;          // [Z][Hd], transposed z_mlp weight (written by the host)
     __half* za16 = (__half*)a.ws_za16;
@@ -89,6 +100,12 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
 
     RingF ring;
     ring.init(smem, (uint64_t*)(smem + OFF_BAR));
+    if (tid == 0) mbar_init(accbar, 1);
+    if (warp == 0) {                                        // TMEM: 128 columns for the whole kernel
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
 
     // ---- static ownership
     const int u4_0 = (int)((long)c * D / P), u4_1 = (int)((long)(c + 1) * D / P), nu = u4_1 - u4_0;   // B: my hidden units
@@ -104,6 +121,9 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
 
     for (int o = tid; o < nu * BI; o += NT) hcs[(o % nu) * BROWS + o / nu] = __ldcg(a.hin + (long)(o / nu) * D + u4_0 + o % nu);
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    uint32_t accpar = 0;
 
     auto job_b = [&]() {
         JobF j; j.ntile = nu > 0 ? 3 : 0; j.nx = 1; j.xmap[0] = &maps.za; j.xmap[1] = &maps.za; j.xrow0 = 0; j.xrows = BROWS; j.xf16 = 1;
@@ -112,7 +132,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         return j;
     };
     auto job_c = [&]() {
-        JobF j; j.ntile = inC ? MAXT : 0; j.nx = 1; j.xmap[0] = &maps.h; j.xmap[1] = &maps.h; j.xrow0 = 0; j.xrows = BROWS; j.xf16 = 1;
+        JobF j; j.ntile = inC ? 14 : 0; j.nx = 1; j.xmap[0] = &maps.h; j.xmap[1] = &maps.h; j.xrow0 = 0; j.xrows = BROWS; j.xf16 = 1;
         j.kcol0 = ks * kslice; j.nkb = j.ntile ? (kslice + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < 12; ++i) { j.wmap[i] = &maps.whh; j.row0[i] = (i / 4) * D + u6_0 + 16 * (i % 4); }   // tile = gate * 4 + i
         for (int i = 0; i < 2; ++i) { j.wmap[12 + i] = &maps.wph; j.row0[12 + i] = f6_0 + 16 * i; }
@@ -150,29 +170,34 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
     // phase C: partial products of my rows over my k slice -> global (gh partials only when want_gh, y2 partials when want_y2)
     auto phase_c = [&](bool want_gh, bool want_y2) {
         const JobF j = job_c();
-        float acc[4][4][4];
-        // 8 warps = 4 tile groups (gate r, gate u, gate n, W_ph rows) x 2 batch halves
-        const int grp = warp & 3, half = warp >> 2;
-        const bool act = j.nkb > 0 && half * 32 < BI;
-        consume_f16<4, 4>(ring, j, 4 * grp, 4 * half, act, acc);
-        if (!act) return;
-        const int g = lane >> 2, tq = lane & 3;
+        if (j.nkb == 0) return;
+        consume_umma<2, 64>(ring, j, tmem, accbar, accpar);
+        accpar ^= 1;
+        // warp w reads UMMA tile (w >> 2), TMEM lane quarter (w & 3): thread = one weight row x 64 batch columns
+        const int ut = warp >> 2, quarter = warp & 3;
+        const int urow = quarter * 32 + lane, slot = ut * 8 + (urow >> 4), rr = urow & 15;
+        float* dst = nullptr;                                   // element b of my row goes to dst[b * bstride]
+        long bstride = 0;
+        if (slot < 12) {
+            const int gate = slot >> 2, u = u6_0 + (slot & 3) * 16 + rr;
+            if (want_gh && u < u6_1) { dst = a.ws_ghpart + ((long)u * 3 + gate) * KS + ks; bstride = (long)D * 3 * KS; }
+        } else if (slot < 14) {
+            const int f = f6_0 + (slot - 12) * 16 + rr;
+            if (want_y2 && f < f6_1) { dst = a.ws_y2part + (long)f * KS + ks; bstride = (long)Hd * KS; }
+        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int cc = 0; cc < 2; ++cc) {
+            uint32_t r[32];
+            tc_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ut * 64 + cc * 32), r);
+            if (dst) {
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = 16 * i + g + 8 * (e >> 1), b = (4 * half + jn) * 8 + 2 * tq + (e & 1);
-                    if (b >= BI) continue;
-                    if (grp < 3) {
-                        const int u = u6_0 + r;
-                        if (want_gh && u < u6_1) a.ws_ghpart[((long)ks * BI + b) * D3 + (long)grp * D + u] = acc[i][jn][e];
-                    } else {
-                        const int f = f6_0 + r;
-                        if (want_y2 && i < 2 && f < f6_1) a.ws_y2part[((long)ks * BI + b) * Hd + f] = acc[i][jn][e];
-                    }
+                for (int jb = 0; jb < 32; ++jb) {
+                    const int b = cc * 32 + jb;
+                    if (b < BI) dst[(long)b * bstride] = __uint_as_float(r[jb]);
                 }
+            }
+        }
+        tc_fence_before();
     };
 
     // ---- prologue: fp16 h_0 for the TMA reads of the first recurrent product
@@ -245,41 +270,53 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         // ---- phase B (hidden-unit owners): gi = za . W_ih^T, GRU gate math, h' -> feat / hin[t+1] / h16
         {
             const JobF j = job_b();
-            float acc[3][2][4];
-            const bool act = warp < 4 && j.nkb > 0 && warp * 16 < BI;          // warp = pair of n8-tiles of batch rows
-            consume_f16<3, 2>(ring, j, 0, 2 * warp, act, acc);
-            if (act) {
-                const int g = lane >> 2, tq = lane & 3;
+            if (j.nkb > 0) {
+                consume_umma<1, 64>(ring, j, tmem, accbar, accpar);
+                accpar ^= 1;
+                // rows 0..47 of the UMMA tile = (gate, unit): quarters 0 and 1; warps w and w + 4 take 32 batch columns each
+                if ((warp & 3) < 2) {
+                    const int quarter = warp & 3, cc = warp >> 2, urow = quarter * 32 + lane;
+                    uint32_t r[32];
+                    tc_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
+                    if (urow < 48) {
 #pragma unroll
-                for (int jn = 0; jn < 2; ++jn)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int r = g + 8 * (e >> 1), b = (2 * warp + jn) * 8 + 2 * tq + (e & 1), u = u4_0 + r;
-                        if (r >= nu || b >= BI) continue;
-                        const long row = (long)t * BI + b;
-                        const float m = t > 0 ? a.mask[row] : 1.f;              // h_0 arrives already masked
-                        const float mn = t + 1 < T ? a.mask[row + BI] : 0.f;
-                        float gh0 = 0.f, gh1 = 0.f, gh2 = 0.f;
-                        for (int k = 0; k < KS; ++k) {
-                            const float* gp = a.ws_ghpart + ((long)k * BI + b) * D3 + u;
-                            gh0 += __ldcg(gp); gh1 += __ldcg(gp + D); gh2 += __ldcg(gp + 2 * D);
-                        }
-                        const float ghr = m * gh0 + a.b_hh[u];
-                        const float ghu = m * gh1 + a.b_hh[D + u];
-                        const float ghn = m * gh2 + a.b_hh[2 * D + u];
-                        const float rg_ = pd_sigmoid(acc[0][jn][e] + a.b_ih[u] + ghr);
-                        const float ug_ = pd_sigmoid(acc[1][jn][e] + a.b_ih[D + u] + ghu);
-                        const float ng_ = tanhf(acc[2][jn][e] + a.b_ih[2 * D + u] + rg_ * ghn);
-                        const float hp = hcs[r * BROWS + b];
-                        const __half hh = __float2half_rn((1.f - ug_) * ng_ + ug_ * hp);
-                        const float hn = __half2float(hh);
-                        a.feat[row * F + u] = hn;
-                        h16[(long)b * D + u] = hh;
-                        hcs[r * BROWS + b] = hn * mn;
-                        if (t + 1 < T) a.hin[(row + BI) * D + u] = hn * mn;
-                        float* gt = a.gates + row * 4 * D;
-                        gt[u] = rg_; gt[D + u] = ug_; gt[2 * D + u] = ng_; gt[3 * D + u] = ghn;
+                        for (int jb = 0; jb < 32; ++jb) gis[urow * 65 + cc * 32 + jb] = __uint_as_float(r[jb]);
                     }
+                }
+                tc_fence_before();
+                cons_sync();
+                // gate math: one (unit, batch row) per thread iteration, unit fastest (coalesced global accesses)
+                for (int o = tid; o < nu * BI; o += NCT) {
+                    const int r = o % nu, b = o / nu, u = u4_0 + r;
+                    const long row = (long)t * BI + b;
+                    const float m = t > 0 ? a.mask[row] : 1.f;              // h_0 arrives already masked
+                    const float mn = t + 1 < T ? a.mask[row + BI] : 0.f;
+                    float gh0 = 0.f, gh1 = 0.f, gh2 = 0.f;
+                    const float* gp = a.ws_ghpart + ((long)b * D + u) * 3 * KS;
+                    if (KS == 4) {
+                        const float4 q0 = __ldcg(reinterpret_cast<const float4*>(gp));
+                        const float4 q1 = __ldcg(reinterpret_cast<const float4*>(gp) + 1);
+                        const float4 q2 = __ldcg(reinterpret_cast<const float4*>(gp) + 2);
+                        gh0 = (q0.x + q0.y) + (q0.z + q0.w); gh1 = (q1.x + q1.y) + (q1.z + q1.w); gh2 = (q2.x + q2.y) + (q2.z + q2.w);
+                    } else {
+                        for (int k = 0; k < KS; ++k) { gh0 += __ldcg(gp + k); gh1 += __ldcg(gp + KS + k); gh2 += __ldcg(gp + 2 * KS + k); }
+                    }
+                    const float ghr = m * gh0 + a.b_hh[u];
+                    const float ghu = m * gh1 + a.b_hh[D + u];
+                    const float ghn = m * gh2 + a.b_hh[2 * D + u];
+                    const float rg_ = pd_sigmoid(gis[(0 * 16 + r) * 65 + b] + a.b_ih[u] + ghr);
+                    const float ug_ = pd_sigmoid(gis[(1 * 16 + r) * 65 + b] + a.b_ih[D + u] + ghu);
+                    const float ng_ = tanhf(gis[(2 * 16 + r) * 65 + b] + a.b_ih[2 * D + u] + rg_ * ghn);
+                    const float hp = hcs[r * BROWS + b];
+                    const __half hh = __float2half_rn((1.f - ug_) * ng_ + ug_ * hp);
+                    const float hn = __half2float(hh);
+                    a.feat[row * F + u] = hn;
+                    h16[(long)b * D + u] = hh;
+                    hcs[r * BROWS + b] = hn * mn;
+                    if (t + 1 < T) a.hin[(row + BI) * D + u] = hn * mn;
+                    float* gt = a.gates + row * 4 * D;
+                    gt[u] = rg_; gt[D + u] = ug_; gt[2 * D + u] = ng_; gt[3 * D + u] = ghn;
+                }
             }
         }
         grid_barrier(a.ws_barrier, epoch);                                      // (2) h' complete
@@ -301,7 +338,13 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
                 v[i] = 0.f;
                 if (f < Hd) {
                     float s = a.b_ph[f] + (a.ea ? a.ea[((long)t * Bq + b / a.I) * Hd + f] : 0.f);
-                    for (int k = 0; k < KS; ++k) s += __ldcg(a.ws_y2part + ((long)k * BI + b) * Hd + f);
+                    const float* yp = a.ws_y2part + ((long)b * Hd + f) * KS;
+                    if (KS == 4) {
+                        const float4 q = __ldcg(reinterpret_cast<const float4*>(yp));
+                        s += (q.x + q.y) + (q.z + q.w);
+                    } else {
+                        for (int k = 0; k < KS; ++k) s += __ldcg(yp + k);
+                    }
                     v[i] = s;
                     a.y2[row * Hd + f] = s;
                 }
@@ -362,6 +405,9 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         if (t + 1 < T) grid_barrier(a.ws_barrier, epoch);                       // (5) idx_t complete
         clk.lap(5);
     }
+    tc_fence_before();
+    cons_sync();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 }  // namespace

@@ -85,5 +85,6 @@ def test_sass_of_the_persistent_rssm_kernel():
                           capture_output=True, text=True).stdout
     if "HMMA" not in sass:                       # older cuobjdump: -fun wants the mangled name; fall back to the whole file
         sass = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
-    assert "HMMA.16816.F32" in sass              # mma.sync.m16n8k16 f16 -> f32
-    assert "UTMALDG.2D" in sass and "LDSM" in sass   # TMA tile staging, ldmatrix operand reads
+    assert "UTCHMMA" in sass and "LDTM" in sass  # tcgen05.mma kind::f16 for the wide contractions, tcgen05.ld epilogues
+    assert "UTMALDG.2D" in sass                  # TMA tile staging
+    assert "HMMA.16816.F32" in sass and "LDSM" in sass   # the small logits contraction stays on mma.sync + ldmatrix
