@@ -87,13 +87,13 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
     epoch += 1;
     if (threadIdx.x == 0) {
         const unsigned target = epoch * gridDim.x;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // release-arrive / acquire-poll: the bar.sync above orders the CTA's writes before this thread's release (cumulative
+        // at gpu scope), the bar.sync below hands what the acquire observed to the rest of the CTA
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned spins = 0;
         while (ld_acquire(ctr) < target) {
             if (++spins > (1u << 24)) __trap();                 // ~10 s: a lost CTA must not hang the device
         }
-        __threadfence();
     }
     cons_sync();
 }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool producer = warp == NCW;
     const int P = gridDim.x, c = blockIdx.x;
-    const int T = a.T, BI = a.BI, D = a.D, Hd = a.Hd, G = a.G, C = a.C, Z = G * C, F = D + Z;
+    const int T = a.T, BI = a.BI, D = a.D, Hd = a.Hd, G = a.G, C = a.C, Z = G * C, F = D + Z, D3 = 3 * D;
     const int Bq = BI / a.I;                                // sequences (rows of aa / ea per timestep)
     const __half* wzT = (const __half*)a.ws_wzT16;          // [Z][Hd], transposed z_mlp weight (written by the host)
     __half* za16 = (__half*)a.ws_za16;
@@ -176,14 +176,15 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         // warp w reads UMMA tile (w >> 2), TMEM lane quarter (w & 3): thread = one weight row x 64 batch columns
         const int ut = warp >> 2, quarter = warp & 3;
         const int urow = quarter * 32 + lane, slot = ut * 8 + (urow >> 4), rr = urow & 15;
-        float* dst = nullptr;                                   // element b of my row goes to dst[b * bstride]
+        float* dst = nullptr;                                   // element b of my row goes to dst[b * bstride]: partial planes
+                                                                // [ks][b][row], lanes = consecutive rows -> coalesced stores
         long bstride = 0;
         if (slot < 12) {
             const int gate = slot >> 2, u = u6_0 + (slot & 3) * 16 + rr;
-            if (want_gh && u < u6_1) { dst = a.ws_ghpart + ((long)u * 3 + gate) * KS + ks; bstride = (long)D * 3 * KS; }
+            if (want_gh && u < u6_1) { dst = a.ws_ghpart + (long)ks * BI * D3 + (long)gate * D + u; bstride = D3; }
         } else if (slot < 14) {
             const int f = f6_0 + (slot - 12) * 16 + rr;
-            if (want_y2 && f < f6_1) { dst = a.ws_y2part + (long)f * KS + ks; bstride = (long)Hd * KS; }
+            if (want_y2 && f < f6_1) { dst = a.ws_y2part + (long)ks * BI * Hd + f; bstride = Hd; }
         }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -292,14 +293,9 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
                     const float m = t > 0 ? a.mask[row] : 1.f;              // h_0 arrives already masked
                     const float mn = t + 1 < T ? a.mask[row + BI] : 0.f;
                     float gh0 = 0.f, gh1 = 0.f, gh2 = 0.f;
-                    const float* gp = a.ws_ghpart + ((long)b * D + u) * 3 * KS;
-                    if (KS == 4) {
-                        const float4 q0 = __ldcg(reinterpret_cast<const float4*>(gp));
-                        const float4 q1 = __ldcg(reinterpret_cast<const float4*>(gp) + 1);
-                        const float4 q2 = __ldcg(reinterpret_cast<const float4*>(gp) + 2);
-                        gh0 = (q0.x + q0.y) + (q0.z + q0.w); gh1 = (q1.x + q1.y) + (q1.z + q1.w); gh2 = (q2.x + q2.y) + (q2.z + q2.w);
-                    } else {
-                        for (int k = 0; k < KS; ++k) { gh0 += __ldcg(gp + k); gh1 += __ldcg(gp + KS + k); gh2 += __ldcg(gp + 2 * KS + k); }
+                    for (int k = 0; k < KS; ++k) {                          // k-slice partials of phase C (threads run over u: coalesced)
+                        const float* gp = a.ws_ghpart + ((long)k * BI + b) * D3 + u;
+                        gh0 += __ldcg(gp); gh1 += __ldcg(gp + D); gh2 += __ldcg(gp + 2 * D);
                     }
                     const float ghr = m * gh0 + a.b_hh[u];
                     const float ghu = m * gh1 + a.b_hh[D + u];
@@ -338,13 +334,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
                 v[i] = 0.f;
                 if (f < Hd) {
                     float s = a.b_ph[f] + (a.ea ? a.ea[((long)t * Bq + b / a.I) * Hd + f] : 0.f);
-                    const float* yp = a.ws_y2part + ((long)b * Hd + f) * KS;
-                    if (KS == 4) {
-                        const float4 q = __ldcg(reinterpret_cast<const float4*>(yp));
-                        s += (q.x + q.y) + (q.z + q.w);
-                    } else {
-                        for (int k = 0; k < KS; ++k) s += __ldcg(yp + k);
-                    }
+                    for (int k = 0; k < KS; ++k) s += __ldcg(a.ws_y2part + ((long)k * BI + b) * Hd + f);
                     v[i] = s;
                     a.y2[row * Hd + f] = s;
                 }
