@@ -304,7 +304,9 @@ int pd_onehot_i64(pd_handle* h, long rows, int A, const int64_t* idx, float* out
 int pd_tanh(pd_handle* h, long n, const float* x, float* y, void* stream);
 
 /* ---- optimizer (dreamer.py:60-87, train.py:193-198) ---------------------------------------- */
-int pd_sumsq(pd_handle* h, const float* x, long n, float* out /* += */, void* stream);
+/* out += sum x^2 in a fixed summation order (bit-identical on every data-parallel replica); ws: pd_sumsq_ws_floats(h) floats */
+int pd_sumsq(pd_handle* h, const float* x, long n, float* out /* += */, float* ws, void* stream);
+int pd_sumsq_ws_floats(const pd_handle* h);
 /* norm = sqrt(*sumsq); coef = min(1, max_norm/(norm+1e-6)); x *= coef; *norm_out = norm
  * (== torch.nn.utils.clip_grad_norm_). */
 int pd_clip_scale(pd_handle* h, float* x, long n, const float* sumsq, float max_norm, float* norm_out, void* stream);

@@ -332,12 +332,22 @@ __global__ void tanh_normal_sample_kernel(long rows, int A, const float* __restr
 }
 
 // ------------------------------------------------------------------ optimizer
-__global__ void sumsq_kernel(const float* __restrict__ x, long n, float* out) {
+// Sum of squares in a FIXED summation order (block partials to a workspace, then one block adds them up): data-parallel
+// replicas compute the clip coefficient from bit-identical all-reduced gradients and must get bit-identical norms, or the
+// replicas drift apart by an ulp per clipped step (an atomicAdd over blocks sums in arrival order).
+__global__ void sumsq_partial_kernel(const float* __restrict__ x, long n, float* __restrict__ partial) {
     __shared__ float sh[33];
     float acc = 0.f;
     GRID_STRIDE(i, n) { float v = x[i]; acc += v * v; }
     float s = pd_block_sum(acc, sh);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ partial, int np, float* out) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += partial[i];
+    float s = pd_block_sum(acc, sh);
+    if (threadIdx.x == 0) *out += s;
 }
 __global__ void clip_scale_kernel(float* __restrict__ x, long n, const float* __restrict__ sumsq, float max_norm,
                                   float* norm_out) {
@@ -497,13 +507,17 @@ int pd_tanh_normal_sample(pd_handle* h, long rows, int A, const float* out, long
     PD_CHECK_LAUNCH(h, "tanh_normal_sample");
     return PD_OK;
 }
-int pd_sumsq(pd_handle* h, const float* x, long n, float* out, void* stream) {
+int pd_sumsq(pd_handle* h, const float* x, long n, float* out, float* ws, void* stream) {
+    PD_REQUIRE(h, ws, "pd_sumsq: workspace of pd_sumsq_ws_floats() floats required");
     int grid = grid_for(n, 256, h->num_sms);
     if (grid > 4 * h->num_sms) grid = 4 * h->num_sms;
-    sumsq_kernel<<<grid, 256, 0, S(stream)>>>(x, n, out);
-    PD_CHECK_LAUNCH(h, "sumsq");
+    sumsq_partial_kernel<<<grid, 256, 0, S(stream)>>>(x, n, ws);
+    PD_CHECK_LAUNCH(h, "sumsq_partial");
+    sumsq_final_kernel<<<1, 256, 0, S(stream)>>>(ws, grid, out);
+    PD_CHECK_LAUNCH(h, "sumsq_final");
     return PD_OK;
 }
+int pd_sumsq_ws_floats(const pd_handle* h) { return h ? 4 * h->num_sms : 0; }
 int pd_clip_scale(pd_handle* h, float* x, long n, const float* sumsq, float max_norm, float* norm_out, void* stream) {
     clip_scale_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, S(stream)>>>(x, n, sumsq, max_norm, norm_out);
     PD_CHECK_LAUNCH(h, "clip_scale");

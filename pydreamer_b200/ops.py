@@ -385,7 +385,10 @@ class NativeOps:
     # ------------------------------------------------------------------ optimizer
     def sumsq(self, x, out):
         assert x.is_contiguous()
-        self._ck(self.lib.pd_sumsq(self.h, _ptr(x), x.numel(), _ptr(out), self._s()), "pd_sumsq")
+        ws = getattr(self, "_sumsq_ws", None)
+        if ws is None:
+            ws = self._sumsq_ws = torch.empty(int(self.lib.pd_sumsq_ws_floats(self.h)), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.pd_sumsq(self.h, _ptr(x), x.numel(), _ptr(out), _ptr(ws), self._s()), "pd_sumsq")
 
     def clip_scale(self, x, sumsq, max_norm, norm_out):
         self._ck(self.lib.pd_clip_scale(self.h, _ptr(x), x.numel(), _ptr(sumsq), float(max_norm), _ptr(norm_out),

@@ -59,8 +59,9 @@ def _worker(rank, port, out):
     gathered = [torch.empty_like(flat) for _ in range(WORLD)]
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], g) for g in gathered)
+    maxdiff = max(float((gathered[0] - g).abs().max()) for g in gathered)
     if rank == 0:
-        torch.save(dict(norms=norms, same=same, params={k: v.cpu().clone() for k, v in model.state_dict().items()}), out)
+        torch.save(dict(norms=norms, same=same, maxdiff=maxdiff, params={k: v.cpu().clone() for k, v in model.state_dict().items()}), out)
     dist.destroy_process_group()
 
 
@@ -70,7 +71,7 @@ def test_two_rank_nccl_matches_single_gpu_global_batch(tmp_path):
     port = 29600 + os.getpid() % 2000
     mp.spawn(_worker, args=(port, out), nprocs=WORLD, join=True)
     got = torch.load(out)
-    assert got["same"], "ranks diverged after one data-parallel step"
+    assert got["same"], f"ranks diverged after one data-parallel step (max |delta| {got['maxdiff']:.3e})"
     dev = "cuda:0"
     conf, obs, noise = _inputs()
     conf = make_conf("tiny", device=dev, batch_size=BG)
