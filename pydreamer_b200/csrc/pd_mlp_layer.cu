@@ -8,8 +8,10 @@
 // whole TMEM (512 columns x 128 lanes x fp32).  Pipeline (persistent, one CTA per SM):
 //   warp 0     TMA producer: A tile [128 x 64 halfs] + the full weight slab [N x 64 halfs] per k-block, 128-byte swizzle
 //   warp 1     tcgen05.mma.kind::f16, M = 128, N in one or two instructions (256 + N - 256), accumulator in TMEM
-//   warps 2-5  epilogue, thread = row: pass 1 reads the row from TMEM (+bias) for mean / variance, pass 2 re-reads it,
-//              normalises, applies ELU and stores fp16 (and, for layers whose backward needs them, fp32 x / y / mean / rstd)
+//   warps 2-9  epilogue, thread = row, two warps per TMEM lane quarter split the columns: pass 1 reads the row from TMEM
+//              (+bias) for mean / variance (partial sums exchanged through shared memory), pass 2 re-reads it, normalises,
+//              applies ELU and stores fp16 (and, for layers whose backward needs them, fp32 x / y / mean / rstd);
+//              bias / gamma / beta live in shared memory
 #include "pd_common.cuh"
 #include <cuda_fp16.h>
 
@@ -18,7 +20,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int KB = 64;                          // halfs per k-block (128-byte rows)
 constexpr int A_BYTES = BM * 128;               // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 
 struct MlpArgs {
@@ -98,6 +101,9 @@ pd_mlp_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tfull = bars + 8;
     uint64_t* tempty = bars + 9;
     uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+    float* prm = (float*)(bars + 16);             // [3][N]: bias, gamma, beta
+    float* xch = prm + 3 * g.N;                   // [2 halves][128 rows][2]: partial (sum, sumsq) of a row
+    for (int i = threadIdx.x; i < g.N; i += NUM_THREADS) { prm[i] = g.bias[i]; prm[g.N + i] = g.gamma[i]; prm[2 * g.N + i] = g.beta[i]; }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -105,7 +111,7 @@ pd_mlp_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB1) : "memory");
         for (int i = 0; i < g.nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(tfull, 1);
-        mbar_init(tempty, 4);
+        mbar_init(tempty, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -163,38 +169,46 @@ pd_mlp_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        const int quarter = warp & 3;
+        const int quarter = warp & 3, half = (warp - 2) >> 2;       // two warps per lane quarter: column halves
         uint32_t tphase = 0;
         const int nchunk = (g.N + 31) / 32;
+        const int c_lo = half == 0 ? 0 : (nchunk + 1) / 2, c_hi = half == 0 ? (nchunk + 1) / 2 : nchunk;
         const float invN = 1.f / (float)g.N;
+        const float *sbias = prm, *sgam = prm + g.N, *sbet = prm + 2 * g.N;
+        const int rloc = quarter * 32 + lane;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             mbar_wait(tfull, tphase);
             tc_fence_after();
-            const long row = (long)tile * BM + quarter * 32 + lane;
+            const long row = (long)tile * BM + rloc;
             const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16);
-            // ---- pass 1: row statistics of (acc + bias)
+            // ---- pass 1: partial row statistics of (acc + bias) over my columns
             float s = 0.f, q = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < nchunk; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int col = c * 32 + j;
                     if (col < g.N) {
-                        const float v = __uint_as_float(r[j]) + __ldg(g.bias + col);
+                        const float v = __uint_as_float(r[j]) + sbias[col];
                         s += v; q += v * v;
                     }
                 }
             }
+            xch[(half * BM + rloc) * 2] = s;
+            xch[(half * BM + rloc) * 2 + 1] = q;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // the two warps of this quarter
+            s += xch[((half ^ 1) * BM + rloc) * 2];
+            q += xch[((half ^ 1) * BM + rloc) * 2 + 1];
             const float mean = s * invN;
             const float var = fmaxf(q * invN - mean * mean, 0.f);
             const float rstd = 1.0f / sqrtf(var + g.eps);
             const bool live = row < g.M;
-            if (live && g.mean) { g.mean[row] = mean; g.rstd[row] = rstd; }
+            if (live && g.mean && half == 0) { g.mean[row] = mean; g.rstd[row] = rstd; }
             // ---- pass 2: normalise, ELU, store
 #pragma unroll 1
-            for (int c = 0; c < nchunk; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);
                 const int col0 = c * 32;
@@ -204,8 +218,8 @@ pd_mlp_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int j = 0; j < 32; ++j) {
                     const int col = col0 + j;
                     if (col < g.N) {
-                        xv[j] = __uint_as_float(r[j]) + __ldg(g.bias + col);
-                        const __half hv = __float2half_rn(pd_elu((xv[j] - mean) * rstd * __ldg(g.gamma + col) + __ldg(g.beta + col)));
+                        xv[j] = __uint_as_float(r[j]) + sbias[col];
+                        const __half hv = __float2half_rn(pd_elu((xv[j] - mean) * rstd * sgam[col] + sbet[col]));
                         yv[j] = __half2float(hv);
                     } else { xv[j] = 0.f; yv[j] = 0.f; }
                 }
@@ -244,7 +258,7 @@ pd_mlp_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
             tc_fence_before();
-            __syncwarp();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // xch is reused by the next tile
             if (lane == 0) mbar_arrive(tempty);
             tphase ^= 1;
         }
@@ -295,7 +309,11 @@ extern "C" int pd_mlp_layer_f16(pd_handle* h, int M, int N, int K, const void* A
     if (!rc && N2 > 0) rc = f16_map(h, &tmB2, W16, N, K, ldw, N2);
     if (rc) return rc;
     if (N2 == 0) tmB2 = tmB1;
-    const int smem = g.nstage * g.stage_bytes + 1024 + 128;
+    const int extra = 128 + 3 * N * 4 + 2 * BM * 2 * 4;         // barriers, bias / gamma / beta, row-statistics exchange
+    g.nstage = (h->max_smem_optin - 2048 - extra) / g.stage_bytes;
+    if (g.nstage > 4) g.nstage = 4;
+    PD_REQUIRE(h, g.nstage >= 2, "pd_mlp_layer_f16: N = %d needs %d bytes per stage", N, g.stage_bytes);
+    const int smem = g.nstage * g.stage_bytes + 1024 + extra;
     if (!h->mlp_smem_configured) {                            // once per handle: opt in to the device's full shared memory
         cudaError_t e = cudaFuncSetAttribute(pd_mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "pd_mlp_layer_f16: cudaFuncSetAttribute(smem=%d): %s", h->max_smem_optin, cudaGetErrorString(e));
