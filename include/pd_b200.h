@@ -130,14 +130,6 @@ int pd_cat_st_bwd(pd_handle* h, int M, int G, int C, const float* logits, long l
                   const float* extra, long ldex, const float* rowscale, float alpha,
                   float* dlogits, long lddl, void* stream);
 
-/* ---- one hidden MLP layer, fused: Y = ELU(LayerNorm(A . W^T + bias)) (common.py:42-51) with fp16 operands ------------- */
-/* Row-complete tiles (128 rows x all N <= 512 columns in TMEM), tcgen05.mma kind::f16, LayerNorm(eps) + ELU in the epilogue
- * (csrc/pd_mlp_layer.cu).  A16 [M,K] fp16, W16 [N,K] fp16 (nn.Linear layout), N %% 16 == 0.  Outputs: y16 fp16 (next layer's
- * operand) and, optionally (layers whose backward runs), fp32 y (fp16-representable), fp32 pre-norm x, mean / rstd [M]. */
-int pd_mlp_layer_f16(pd_handle* h, int M, int N, int K, const void* A16, long lda, const void* W16, long ldw,
-                     const float* bias, const float* gamma, const float* beta, float eps, void* y16, long ldy16,
-                     float* y, long ldy, float* x, long ldx, float* mean, float* rstd, void* stream);
-
 /* ---- persistent RSSM posterior unroll (rssm.py:21-78 RSSMCore.forward, 125-153 RSSMCell.forward) -------------
  * ONE cooperative kernel walks all T timesteps (csrc/pd_rssm_fwd3.cu): per step { z_mlp as a gather over the sampled
  * one-hot + a_mlp term -> LayerNorm+ELU -> GRU gates -> post_mlp_h + embed term -> LayerNorm+ELU -> post_mlp ->

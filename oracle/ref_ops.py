@@ -114,21 +114,6 @@ class RefOps:
             dbias.add_(d.sum(0))
         dx.copy_(d)
 
-    def mlp_layer_f16(self, A16, W16, bias, gamma, beta, eps, y16=None, y=None, x=None, mean=None, rstd=None):
-        dt = bias.dtype
-        xv = A16.to(dt) @ W16.to(dt).t() + bias
-        mu, var = xv.mean(-1), xv.var(-1, unbiased=False)
-        r = 1.0 / torch.sqrt(var + eps)
-        yv = F.elu((xv - mu[:, None]) * r[:, None] * gamma + beta).to(torch.float16)
-        if y16 is not None:
-            y16.copy_(yv)
-        if y is not None:
-            y.copy_(yv.to(dt))
-        if x is not None:
-            x.copy_(xv)
-        if mean is not None:
-            mean.copy_(mu); rstd.copy_(r)
-
     def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None, h16=None):
         D = hprev.shape[1]
         r = torch.sigmoid(gi[:, :D] + gh[:, :D])

@@ -29,7 +29,6 @@ struct pd_handle {
     int k1_ctas;              // ... and the co-resident grid they launch (one CTA per SM)
     int k1b_configured;
     int k1b_ctas;
-    int mlp_smem_configured;
 };
 
 // Launch wrappers run on the handle's device whatever the caller's current device is (and put it back).

@@ -432,8 +432,6 @@ class Dreamer(nn.Module):
     # forward-only layers (imagination rollout, heads on dreamed features) use fp16 tensor-core operands: the same
     # 10-bit mantissa as TF32 at twice the MMA rate and half the operand traffic; no gradient flows through them.
     fp16_forward = os.environ.get("PD_B200_FP16_FORWARD", "1") != "0"
-    # hidden MLP layers on the fp16-forward path as one fused kernel (Linear + LayerNorm + ELU, csrc/pd_mlp_layer.cu)
-    fused_mlp = os.environ.get("PD_B200_FUSED_MLP", "1") != "0"
     # conv / deconv contractions gather their operand with TMA im2col-mode loads (pd_conv_gemm) instead of materialising
     # im2col matrices: encoder layers 2-4 (forward + weight gradient), deconv layers 2-3 (input + weight gradient).
     implicit_conv = os.environ.get("PD_B200_IMPLICIT_CONV", "1") != "0"
@@ -601,15 +599,6 @@ class Dreamer(nn.Module):
                 y = self._buf(f"{self._scratch_ns}mlp.sy{l % 2}", rows, mp.hid)
                 mean = self._buf(f"{self._scratch_ns}mlp.sm", rows)
                 rstd = self._buf(f"{self._scratch_ns}mlp.sr", rows)
-            if f16 and self.fused_mlp and mp.hid <= 512 and mp.hid % 16 == 0 and inp16.shape[1] % 8 == 0:
-                # Linear + LayerNorm + ELU in one kernel (row-complete TMEM tiles); layers whose backward runs keep x / y / stats
-                y16 = self._buf(f"{self._scratch_ns}mlp.h16_{l % 2}", rows, mp.hid, dtype=torch.float16)
-                ops.mlp_layer_f16(inp16, self._wh(mp.lin[l].weight), self._raw(mp.lin[l].bias), self._raw(mp.ln[l].weight),
-                                  self._raw(mp.ln[l].bias), 1e-3, y16=y16, y=y if (save or l == mp.L - 1) else None,
-                                  x=x if save else None,
-                                  mean=mean if save else None, rstd=rstd if save else None)
-                inp, inp16 = y, y16
-                continue
             if f16:
                 ops.gemm_f16(inp16, self._wh(mp.lin[l].weight), x, bias=self._raw(mp.lin[l].bias))
                 y16 = self._buf(f"{self._scratch_ns}mlp.h16_{l % 2}", rows, mp.hid, dtype=torch.float16)

@@ -173,23 +173,6 @@ class NativeOps:
                                         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ld(dx), _ptr(dgamma),
                                         _ptr(dbeta), _ptr(dbias), self._s()), "pd_ln_elu_bwd")
 
-    def mlp_layer_f16(self, A16, W16, bias, gamma, beta, eps, y16=None, y=None, x=None, mean=None, rstd=None):
-        """y16 / y = ELU(LayerNorm(A16 @ W16.T + bias)) in one kernel (pd_mlp_layer_f16); x = pre-norm, mean / rstd optional."""
-        M, K = A16.shape
-        N = W16.shape[0]
-        assert A16.dtype == torch.float16 and W16.dtype == torch.float16 and W16.shape[1] == K
-        ld = lambda t_: _ld(t_) if t_ is not None else 0
-        prof = self.gemm_profile
-        if prof is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        self._ck(self.lib.pd_mlp_layer_f16(self.h, M, N, K, _ptr(A16), _ld(A16), _ptr(W16), _ld(W16), _ptr(bias), _ptr(gamma),
-                                           _ptr(beta), float(eps), _ptr(y16), ld(y16), _ptr(y), ld(y), _ptr(x), ld(x),
-                                           _ptr(mean), _ptr(rstd), self._s()), "pd_mlp_layer_f16")
-        if prof is not None:
-            e1.record()
-            prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, "f16", "ln", 0)))
-
     def gru_fwd(self, gi, gh, hprev, hout, hmask=None, mask_next=None, gates=None, h16=None):
         M, D = hprev.shape
         self._ck(self.lib.pd_gru_fwd(self.h, M, D, _ptr(gi), _ld(gi), _ptr(gh), _ld(gh), _ptr(hprev), _ld(hprev),
