@@ -226,11 +226,6 @@ int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k,
                       const float* target, int tgt_div,
                       float* dec, float* diff, float* loss, float* csum /* [NB,Cc] per-image channel sums of diff */,
                       void* stream);
-/* First encoder layer without a column matrix (encoders.py:80-81): out NHWC [NB,Hout,Wout,Cout] =
- * ELU(conv4x4/stride2(img NCHW [NB,IC,Hin,Win], W [Cout, IC*16] in (c,kh,kw) order) + bias); IC in {1,3}, Win even.
- * Operands are tf32-rounded like the GEMM path's (image on load, W by the caller); round_out rounds the activation. */
-int pd_conv1_direct_fwd(pd_handle* h, int NB, int IC, int Hin, int Win, int Cout, const float* img,
-                        const float* W, const float* bias, float* out, int round_out, void* stream);
 /* dy <- dy * act'(y) in place (act from output y), db[c] += column sums of the result. */
 int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const float* y, long ldy,
                     int act, float* db, void* stream);

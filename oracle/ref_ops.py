@@ -145,11 +145,6 @@ class RefOps:
         dgh.copy_(torch.cat([dr_pre, du_pre, dn_pre * r], 1))
         dh_carry.copy_(dh * u)
 
-    def conv1_direct_fwd(self, img, W, bias, out, round_out=True):
-        NB, IC, H, Wd = img.shape
-        y = F.conv2d(img, W.view(W.shape[0], IC, 4, 4), bias, stride=2)               # (NB, Cout, Hout, Wout)
-        out.copy_(F.elu(y).permute(0, 2, 3, 1).reshape(out.shape))
-
     def rssm_unroll_fwd(self, dims, eps, **t):
         """Torch statement of pd_rssm_unroll_fwd (csrc/pd_rssm_fwd3.cu; rssm.py:21-78, 125-153): the whole posterior
         unroll in one call, fp16 weights, LayerNorm outputs and h rounded to fp16 (they are the tensor-core operands)."""

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpd_b200.so")
 STAMP = os.path.join(HERE, ".libpd_b200.stamp")
 SOURCES = ["pd_api.cu", "pd_gemm_tcgen05.cu", "pd_gemm_simt.cu", "pd_rowwise.cu", "pd_conv.cu", "pd_misc.cu",
-           "pd_rssm_fwd3.cu", "pd_rssm_bptt.cu", "pd_conv_direct.cu"]
+           "pd_rssm_fwd3.cu", "pd_rssm_bptt.cu"]
 HEADERS = [os.path.join(CSRC, "pd_common.cuh"), os.path.join(CSRC, "pd_k1_pipe.cuh"), os.path.join(HERE, "..", "include", "pd_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -780,10 +780,6 @@ class Dreamer(nn.Module):
     overlap = int(os.environ.get("PD_B200_OVERLAP", "3"))
     _scratch_ns = ""          # name space of the shared MLP scratch buffers (one per concurrent branch)
 
-    # PD_B200_DIRECT_CONV1=1: first encoder layer as a direct kernel (csrc/pd_conv_direct.cu) instead of im2col + GEMM;
-    # written after the round's GPU budget was spent, so it is off until it has been run and measured on a B200.
-    direct_conv1 = os.environ.get("PD_B200_DIRECT_CONV1", "0") != "0"
-
     # The posterior unroll runs as ONE cooperative kernel (csrc/pd_rssm_fwd3.cu) when the shape fits its limits
     # (B*I <= 64 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
     persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "1") != "0"
@@ -909,9 +905,7 @@ class Dreamer(nn.Module):
             for li, (hin_, hout, ci, co) in enumerate(geo):
                 hw = hout * hout
                 act = b(f"enc.a{li}", NB * hw, co)[r0 * hw:r1 * hw]
-                if li == 0 and self.direct_conv1 and IC in (1, 3):
-                    ops.conv1_direct_fwd(img[r0:r1], self._encw[0], self._raw(enc[0].bias), act, round_out=True)
-                elif li > 0 and self.implicit_conv:
+                if li > 0 and self.implicit_conv:
                     ops.conv_gemm(1, x4, 4, self._encw[li], act, bias=self._raw(enc[2 * li].bias), act=ACT_ELU,
                                   round_out=True)
                 else:
@@ -1258,9 +1252,6 @@ class Dreamer(nn.Module):
                 ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
                 if li == 0:
                     col = b(f"enc.col{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
-                    if self.direct_conv1 and IC in (1, 3):       # the forward did not build the column matrix
-                        img_ = obs["image"].reshape(NB, IC, 64, 64)[r0:r1]
-                        ops.im2col(img_.permute(0, 2, 3, 1), 4, 1, col, round_out=True)
                     ops.gemm(da, col, G(enc[0].weight).view(co, 16 * ci), a_mn=True, b_mn=True, accumulate=True)
                     continue
                 if self.implicit_conv:

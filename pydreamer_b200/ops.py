@@ -187,13 +187,6 @@ class NativeOps:
                                      _ld(hprev), _ptr(dgi), _ld(dgi), _ptr(dgh), _ld(dgh), _ptr(dh_carry),
                                      _ld(dh_carry), self._s()), "pd_gru_bwd")
 
-    def conv1_direct_fwd(self, img, W, bias, out, round_out=True):
-        """img (NB,IC,H,W) NCHW, W (Cout, IC*16), out (NB*Hout*Wout, Cout) NHWC rows."""
-        NB, IC, H, Wd = img.shape
-        assert img.is_contiguous() and W.is_contiguous() and out.is_contiguous()
-        self._ck(self.lib.pd_conv1_direct_fwd(self.h, NB, IC, H, Wd, W.shape[0], _ptr(img), _ptr(W), _ptr(bias), _ptr(out),
-                                              int(round_out), self._s()), "pd_conv1_direct_fwd")
-
     def rssm_unroll_fwd(self, dims, eps, **t):
         """Persistent posterior unroll (pd_rssm_unroll_fwd).  dims = dict(T, BI, I, D, Hd, G, C); every other struct
         field is passed as a contiguous tensor (or None) by its field name."""

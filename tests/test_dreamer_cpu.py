@@ -20,13 +20,12 @@ def ref_ops():
     pd_ops.set_ops_for_testing(None)
 
 
-def run_model(case, fp16_forward=False, persistent_rssm=False, direct_conv1=False, persistent_bptt=False):
+def run_model(case, fp16_forward=False, persistent_rssm=False, persistent_bptt=False):
     fx, conf, obs, state, noise = build_case(case)
     model = Dreamer(conf)
     model.fp16_forward = fp16_forward
     model.persistent_rssm = persistent_rssm
     model.persistent_bptt = persistent_bptt
-    model.direct_conv1 = direct_conv1
     model.load_state_dict(seeded_weights(model.state_dict(), fx))
     opts = model.init_optimizers(conf.adam_lr, conf.adam_lr_actor, conf.adam_lr_critic, conf.adam_eps)
     losses, out_state, metrics, tensors, dream = model.training_step(obs, state, noise=noise)
@@ -111,18 +110,6 @@ def test_persistent_bptt_branch_of_the_schedule(ref_ops, case):
         got = float(named[k].grad.double().norm())
         tol = 2e-3 if k.startswith("wm.") else 2e-4
         assert abs(got - want) <= tol * max(want, 1e-6) + 1e-8, (k, got, want)
-
-
-def test_direct_first_conv_branch_of_the_schedule(ref_ops):
-    """Host branch of PD_B200_DIRECT_CONV1 (first conv as one direct call; the column matrix is built in the backward
-    only): same goldens as the im2col + GEMM schedule."""
-    fx, conf, model, opts, losses, out_state, metrics, tensors = run_model("tiny_onehot", direct_conv1=True)
-    for got, want in zip(losses, fx["losses"]):
-        assert abs(float(got.detach().reshape(-1)[0]) - want) <= 2e-5 * max(1.0, abs(want))
-    named = dict(model.named_parameters())
-    for k, want in fx["grad_norms"].items():
-        if "encoder" in k:
-            assert abs(float(named[k].grad.double().norm()) - want) <= 2e-4 * max(want, 1e-6) + 1e-9, k
 
 
 def test_state_dict_roundtrip_and_grad_clip_and_optimizer(ref_ops):

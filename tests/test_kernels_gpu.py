@@ -485,24 +485,3 @@ def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
     assert torch.equal(C2, C2r), f"mode 2 max diff {(C2 - C2r).abs().max().item()}"
     ops.conv_gemm(3, X, k, Ot, C3); ref.conv_gemm(3, X, k, Ot, C3r)
     assert torch.equal(C3, C3r), f"mode 3 max diff {(C3 - C3r).abs().max().item()}"
-
-
-EXPERIMENTAL = os.environ.get("PD_B200_TEST_EXPERIMENTAL", "0") != "0"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL and DEV != "cpu", reason="kernel written after the round's GPU budget was spent: "
-                    "set PD_B200_TEST_EXPERIMENTAL=1 to run it on a B200")
-@pytest.mark.parametrize("NB,IC,H,Cout", [(3, 3, 64, 48), (2, 1, 20, 4), (5, 3, 18, 8)])
-def test_conv1_direct_fwd_against_torch_conv(ops, ref, NB, IC, H, Cout):
-    torch.backends.cudnn.allow_tf32 = False
-    x = rnd(NB, IC, H, H, scale=0.5)
-    w = rnd(Cout, IC * 16, scale=0.2, seed=1)
-    b = rnd(Cout, seed=2)
-    Ho = (H - 4) // 2 + 1
-    want = torch.nn.functional.elu(torch.nn.functional.conv2d(x, w.view(Cout, IC, 4, 4), b, stride=2)).permute(0, 2, 3, 1)
-    got = torch.empty(NB * Ho * Ho, Cout, device=DEV)
-    ops.conv1_direct_fwd(x, w, b, got, round_out=False)
-    close(got.view(NB, Ho, Ho, Cout), want, 1e-5, 1e-5, "conv1 direct")
-    twin = torch.empty_like(got)
-    ref.conv1_direct_fwd(x, w, b, twin, round_out=False)
-    close(got, twin, 1e-5, 1e-5, "conv1 direct vs twin")
