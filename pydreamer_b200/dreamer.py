@@ -737,27 +737,16 @@ class Dreamer(nn.Module):
                 finally:
                     self._scratch_ns = ""
 
-        # The world-model branch is the step's critical path (encoder -> unroll -> decoder -> backward, ~22 ms of kernels against
-        # ~13 ms for the imagination branch): with PD_B200_HP_MAIN=1 it is issued on a HIGH-priority stream, so where both branches
-        # have thread blocks ready the scheduler serves the critical one first and the imagination branch fills what is left.
-        hp = self._hp_stream() if (par and self.hp_main) else None
-        if hp is not None:
-            cur0 = torch.cuda.current_stream(self._arena.device)
-            hp.wait_stream(cur0)
-        with (torch.cuda.stream(hp) if hp is not None else contextlib.nullcontext()):
-            wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"], open_loop,
-                                      noise["image_pred"] if image_pred else None, after_features=after_features)
-            if tm is not None:
-                tm.mark("wm_forward")
-            if want_grad:
-                self._wm_backward(obs, T, B, I, H)
-            if tm is not None:
-                tm.mark("wm_backward")
-            if par:
-                self._join(1)
-        if hp is not None:
-            cur0.wait_stream(hp)
+        wm_out = self._wm_forward(obs, in_state, T, B, I, H, noise["post"], open_loop,
+                                  noise["image_pred"] if image_pred else None, after_features=after_features)
+        if tm is not None:
+            tm.mark("wm_forward")
+        if want_grad:
+            self._wm_backward(obs, T, B, I, H)
+        if tm is not None:
+            tm.mark("wm_backward")
         if par:
+            self._join(1)
             cur = torch.cuda.current_stream(self._arena.device)
             for v in ac_box["out"]["metrics"].values():       # allocated on the side stream, consumed on this one
                 v.record_stream(cur)
@@ -839,15 +828,6 @@ class Dreamer(nn.Module):
         # the r02 two-GPU triage matrix (profiles/r02_dp_triage.md) completed in every combination.  PD_B200_DP_FEATURES=0
         # restores round 1's conservative single-stream / per-timestep-chain schedule under data parallelism.
         return self._dp is None or os.environ.get("PD_B200_DP_FEATURES", "1") != "0"
-
-    hp_main = os.environ.get("PD_B200_HP_MAIN", "0") != "0"
-
-    def _hp_stream(self):
-        st = self.__dict__.setdefault("_hp_streams", {})
-        key = torch.cuda.current_stream(self._arena.device).cuda_stream
-        if key not in st:
-            st[key] = torch.cuda.Stream(device=self._arena.device, priority=-1)
-        return st[key]
 
     def _side(self, k):
         key = (k, torch.cuda.current_stream(self._arena.device).cuda_stream)     # one side stream per (purpose, parent)
