@@ -39,6 +39,7 @@ typedef struct pd_handle pd_handle;
 #define PD_GEMM_TCGEN05 0 /* tcgen05.mma kind::tf32 + TMA + TMEM (default, the product path) */
 #define PD_GEMM_SIMT 1    /* plain fp32 CUDA-core tile kernel: validation arm for the tests  */
 #define PD_GEMM_C_ZEROED 1 /* pd_gemm flags bit */
+#define PD_GEMM_C_F16 2    /* pd_gemm flags bit: C is an fp16 matrix (ldc in halfs); not with accumulate */
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int pd_create(int device_ordinal, pd_handle** out);
@@ -58,7 +59,9 @@ int pd_set_round_operands(pd_handle* h, int on);
  *   accumulate = 1: atomically adds into C (split-K over all SMs; bias/R/act must be off).
  * Replaces every nn.Linear / nn.GRUCell matmul and the conv/deconv contractions:
  * common.py:47-55, rssm.py:103-116,138-146, rnn.py:60-67, encoders.py:80-90, decoders.py:128-155.
- * flags: PD_GEMM_C_ZEROED = the caller has already cleared C (skinny-M launches that split K skip their own clear).
+ * flags: PD_GEMM_C_ZEROED = the caller has already cleared C (skinny-M launches that split K skip their own clear);
+ *        PD_GEMM_C_F16 = C points to an fp16 matrix (the deconvolution column matrices of the decoder forward: they are
+ *        written once and read once, in fp16 they cost half the HBM traffic; decoders.py:149-155).
  * TMA constraints (tcgen05 impl): lda/ldb multiples of 4 elements, base pointers 16-byte aligned. */
 int pd_gemm(pd_handle* h, int M, int N, int K,
             const float* A, long lda, int a_mn,
@@ -226,6 +229,13 @@ int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k,
                       const float* target, int tgt_div,
                       float* dec, float* diff, float* loss, float* csum /* [NB,Cc] per-image channel sums of diff */,
                       void* stream);
+/* The same two folds over an fp16 (col_f16 = 1) or fp32 (0) column matrix; ldcol in elements. */
+int pd_col2im_t(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k, const void* col, long ldcol,
+                int col_f16, const float* bias, int act, int round_out, float* out, long sN, long sY, long sX, long sC,
+                void* stream);
+int pd_col2im_imgloss_t(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, const void* col, long ldcol, int col_f16,
+                        const float* bias, const float* target, int tgt_div, float* dec, float* diff, float* loss,
+                        float* csum, void* stream);
 /* dy <- dy * act'(y) in place (act from output y), db[c] += column sums of the result. */
 int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const float* y, long ldy,
                     int act, float* db, void* stream);

@@ -317,14 +317,14 @@ class RefOps:
 
     def col2im(self, col, Hin, Win, k, bias, act, out, round_out=True):
         NB, Hout, Wout, Cc = out.shape
-        v = self._col2im(col, NB, Hin, Win, Hout, Wout, Cc, k)
+        v = self._col2im(col.to(out.dtype), NB, Hin, Win, Hout, Wout, Cc, k)            # (fp16 column matrices are summed in fp32)
         if bias is not None:
             v = v + bias
         out.copy_(_act(v, act))
 
     def col2im_imgloss(self, col, NB, Hin, Win, Cc, k, bias, target, tgt_div, dec, diff, loss, csum):
         Hout, Wout = (Hin - 1) * 2 + k, (Win - 1) * 2 + k
-        v = self._col2im(col, NB, Hin, Win, Hout, Wout, Cc, k) + bias  # NHWC
+        v = self._col2im(col.to(dec.dtype), NB, Hin, Win, Hout, Wout, Cc, k) + bias  # NHWC
         v = v.permute(0, 3, 1, 2)  # NCHW
         tg = target.reshape(-1, Cc, Hout, Wout)[torch.arange(NB, device=col.device) // tgt_div]
         d = v - tg

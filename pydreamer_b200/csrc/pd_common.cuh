@@ -144,6 +144,7 @@ struct PdEpilogue {
     int round_out;       // round result to tf32 precision
     int accumulate;      // 0: C = v ; 1: atomicAdd(C, v) (split-K safe, no bias/act)
     int c_zeroed;        // caller cleared C already (lets a skinny-M split-K launch skip its memset)
+    int c_f16;           // C is an fp16 matrix (ldc in halfs): the epilogue converts and stores rows with vector stores
 };
 
 __device__ __forceinline__ float pd_epi_value(const PdEpilogue& e, int row, int col, float acc) {

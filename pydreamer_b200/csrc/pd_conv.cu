@@ -4,6 +4,7 @@
 // the image MSE loss and layout permutes fused in.  All HBM-bound: thread <-> one output
 // element with the channel index fastest so that global accesses coalesce.
 #include "pd_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -99,8 +100,19 @@ im2col_v4_kernel(long total4, int Hout, int Wout, int C4, int k, const float* __
     }
 }
 
+// four consecutive channels of a column-matrix row as float4 (fp32 or fp16 storage)
+__device__ __forceinline__ float4 ld_col4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld_col4(const __half* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float ld_col1(const float* p) { return *p; }
+__device__ __forceinline__ float ld_col1(const __half* p) { return __half2float(*p); }
+
+template <typename TC>
 __global__ void col2im_v4_kernel(long total4, int Hin, int Win, int Hout, int Wout, int C4, int k,
-                                 const float* __restrict__ col, long ldcol, const float* __restrict__ bias, int act,
+                                 const TC* __restrict__ col, long ldcol, const float* __restrict__ bias, int act,
                                  int round_out, float* __restrict__ out, long sN, long sY, long sX) {
     const int Cc = C4 * 4;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
@@ -122,8 +134,7 @@ __global__ void col2im_v4_kernel(long total4, int Hin, int Win, int Hout, int Wo
                 const int kw = (x & 1) + 2 * bq;
                 const int ix = (x - kw) >> 1;
                 tap[a * 3 + bq] = (oky && kw < k && ix >= 0 && ix < Win)
-                    ? __ldg(reinterpret_cast<const float4*>(col + ((n * Hin + iy) * Win + ix) * ldcol +
-                                                            (long)(kh * k + kw) * Cc + c4 * 4))
+                    ? ld_col4(col + ((n * Hin + iy) * Win + ix) * ldcol + (long)(kh * k + kw) * Cc + c4 * 4)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
@@ -177,9 +188,9 @@ __global__ void col2im_kernel(long total, int Hin, int Win, int Hout, int Wout, 
 // channels of its output pixel in one pass over the (pixel, tap) pieces of the column matrix (Cc <= 4: the decoder's
 // last layer has 1 or 3), so every 32-byte sector of `col` is fetched once instead of once per channel
 // (r02 ncu: 3.15 GB of DRAM reads for a 0.97 GB column matrix with the channel-outer loop).
-template <int CMAX>
+template <int CMAX, typename TC>
 __global__ void __launch_bounds__(256)
-col2im_imgloss_kernel(int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* __restrict__ col, long ldcol,
+col2im_imgloss_kernel(int Hin, int Win, int Hout, int Wout, int Cc, int k, const TC* __restrict__ col, long ldcol,
                       const float* __restrict__ bias, const float* __restrict__ target, int tgt_div,
                       float* __restrict__ dec, float* __restrict__ diff, float* __restrict__ loss,
                       float* __restrict__ csum) {
@@ -206,10 +217,10 @@ col2im_imgloss_kernel(int Hin, int Win, int Hout, int Wout, int Cc, int k, const
                 const int ix = (x - kw) >> 1;
                 if (ix < 0) break;
                 if (ix >= Win) continue;
-                const float* p = col + ((n * Hin + iy) * Win + ix) * ldcol + (long)(kh * k + kw) * Cc;
+                const TC* p = col + ((n * Hin + iy) * Win + ix) * ldcol + (long)(kh * k + kw) * Cc;
 #pragma unroll
                 for (int c = 0; c < CMAX; ++c)
-                    if (c < Cc) v[c] += p[c];
+                    if (c < Cc) v[c] += ld_col1(p + c);
             }
         }
 #pragma unroll
@@ -321,11 +332,28 @@ int pd_im2col(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, int korder,
 int pd_col2im(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* col, long ldcol,
               const float* bias, int act, int round_out, float* out, long sN, long sY, long sX, long sC,
               void* stream) {
+    return pd_col2im_t(h, NB, Hin, Win, Hout, Wout, Cc, k, col, ldcol, 0, bias, act, round_out, out, sN, sY, sX, sC, stream);
+}
+
+int pd_col2im_t(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k, const void* colv, long ldcol,
+                int col_f16, const float* bias, int act, int round_out, float* out, long sN, long sY, long sX, long sC,
+                void* stream) {
     long total = (long)NB * Hout * Wout * Cc;
+    if (col_f16) {
+        const __half* colh = (const __half*)colv;
+        PD_REQUIRE(h, sC == 1 && (Cc % 4) == 0 && (sN % 4) == 0 && (sY % 4) == 0 && (sX % 4) == 0 && (ldcol % 4) == 0 &&
+                       ((((uintptr_t)out) & 15) == 0) && ((((uintptr_t)colh) & 7) == 0) && (!bias || (((uintptr_t)bias) & 15) == 0),
+                   "pd_col2im: the fp16 column matrix path needs channel counts / strides that are multiples of 4");
+        col2im_v4_kernel<__half><<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+            total / 4, Hin, Win, Hout, Wout, Cc / 4, k, colh, ldcol, bias, act, round_out && h->round_ops, out, sN, sY, sX);
+        PD_CHECK_LAUNCH(h, "col2im_v4(f16)");
+        return PD_OK;
+    }
+    const float* col = (const float*)colv;
     const bool v4 = sC == 1 && (Cc % 4) == 0 && (sN % 4) == 0 && (sY % 4) == 0 && (sX % 4) == 0 && (ldcol % 4) == 0 &&
                     ((((uintptr_t)out) | ((uintptr_t)col)) & 15) == 0 && (!bias || (((uintptr_t)bias) & 15) == 0);
     if (v4) {
-        col2im_v4_kernel<<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        col2im_v4_kernel<float><<<grid_for(total / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
             total / 4, Hin, Win, Hout, Wout, Cc / 4, k, col, ldcol, bias, act, round_out && h->round_ops, out, sN, sY, sX);
         PD_CHECK_LAUNCH(h, "col2im_v4");
         return PD_OK;
@@ -339,13 +367,23 @@ int pd_col2im(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc
 int pd_col2im_imgloss(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, const float* col, long ldcol,
                       const float* bias, const float* target, int tgt_div, float* dec, float* diff, float* loss,
                       float* csum, void* stream) {
+    return pd_col2im_imgloss_t(h, NB, Hin, Win, Cc, k, col, ldcol, 0, bias, target, tgt_div, dec, diff, loss, csum, stream);
+}
+
+int pd_col2im_imgloss_t(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, const void* col, long ldcol, int col_f16,
+                        const float* bias, const float* target, int tgt_div, float* dec, float* diff, float* loss,
+                        float* csum, void* stream) {
     int Hout = (Hin - 1) * 2 + k, Wout = (Win - 1) * 2 + k;
     PD_REQUIRE(h, Cc >= 1 && Cc <= 16, "pd_col2im_imgloss: %d image channels (1..16 supported)", Cc);
     const int div = tgt_div > 0 ? tgt_div : 1;
     cudaStream_t s = (cudaStream_t)stream;
-    if (Cc <= 4)      col2im_imgloss_kernel<4><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target, div, dec, diff, loss, csum);
-    else if (Cc <= 8) col2im_imgloss_kernel<8><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target, div, dec, diff, loss, csum);
-    else              col2im_imgloss_kernel<16><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, target, div, dec, diff, loss, csum);
+#define PD_IMGLOSS(CM, TC) col2im_imgloss_kernel<CM, TC><<<NB, 256, 0, s>>>(Hin, Win, Hout, Wout, Cc, k, (const TC*)col, ldcol, bias, target, div, dec, diff, loss, csum)
+    if (col_f16) {
+        if (Cc <= 4) PD_IMGLOSS(4, __half); else if (Cc <= 8) PD_IMGLOSS(8, __half); else PD_IMGLOSS(16, __half);
+    } else {
+        if (Cc <= 4) PD_IMGLOSS(4, float); else if (Cc <= 8) PD_IMGLOSS(8, float); else PD_IMGLOSS(16, float);
+    }
+#undef PD_IMGLOSS
     PD_CHECK_LAUNCH(h, "col2im_imgloss");
     return PD_OK;
 }

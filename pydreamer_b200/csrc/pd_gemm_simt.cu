@@ -3,6 +3,7 @@
 // either implementation, which separates "is the tensor-core pipeline right" from "is the model
 // math right".  Not used by the product path (pd_create selects PD_GEMM_TCGEN05).
 #include "pd_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 constexpr int TM = 64, TN = 64, TK = 16;
@@ -53,6 +54,10 @@ pd_gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, long sAm, 
         for (int j = 0; j < 4; ++j) {
             int col = n0 + tx * 4 + j;
             if (col >= N) continue;
+            if (e.c_f16) {                                  // fp16 output matrix (ldc in halfs)
+                reinterpret_cast<__half*>(e.C)[(long)row * e.ldc + col] = __float2half_rn(pd_epi_value(e, row, col, acc[i][j]));
+                continue;
+            }
             float* c = e.C + (long)row * e.ldc + col;
             if (e.accumulate) atomicAdd(c, acc[i][j]);
             else *c = pd_epi_value(e, row, col, acc[i][j]);
@@ -114,7 +119,7 @@ __global__ void wcolsum_kernel(int M, int N, long K, const float* __restrict__ A
 int pd_gemm_simt_launch(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B,
                         long ldb, int b_mn, const PdEpilogue& epi, cudaStream_t stream) {
     if (h->gemm_impl != PD_GEMM_SIMT) {      // shape-specialised paths of the product (the validation arm stays generic)
-        if (!epi.accumulate && N <= 4 && !a_mn && !b_mn) {
+        if (!epi.accumulate && !epi.c_f16 && N <= 4 && !a_mn && !b_mn) {
             gemv_rows_kernel<<<pd_cdiv(M, 8), 256, 0, stream>>>(M, N, K, A, lda, B, ldb, epi);
             PD_CHECK_LAUNCH(h, "gemv_rows_kernel");
             return PD_OK;

@@ -19,6 +19,7 @@
 //  MN-major: 32-element x 4-k SWIZZLE_128B_BASE32B atoms (TMA SWIZZLE_128B_ATOM_32B), LBO = 4096 B between
 //            32-wide MN groups, SBO = 512 B between 4-row k groups).
 #include "pd_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -147,6 +148,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)layout << 61;
     return d;
+}
+
+// fp16 output: thread = one row x 32 consecutive columns of the tile; rows of C are written as 64-byte runs
+__device__ __forceinline__ void store_row_f16(const PdEpilogue& e, int M, int N, int row, int col0, const float (&v)[32]) {
+    if (row >= M) return;
+    __half* dst = reinterpret_cast<__half*>(e.C) + (long)row * e.ldc + col0;
+    if (col0 + 32 <= N && (e.ldc & 3) == 0 && (((uintptr_t)e.C) & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __half2 h2[2] = {__floats2half2_rn(v[4 * j], v[4 * j + 1]), __floats2half2_rn(v[4 * j + 2], v[4 * j + 3])};
+            *reinterpret_cast<uint2*>(dst + 4 * j) = *reinterpret_cast<const uint2*>(h2);
+        }
+    } else {
+        for (int j = 0; j < 32; ++j) if (col0 + j < N) dst[j] = __float2half_rn(v[j]);
+    }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -364,6 +380,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
                     }
+                    if (e.c_f16) { store_row_f16(e, g.M, g.N, row, col0, v); continue; }
                     uint8_t* buf = stg0 + sbuf * 4096;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer free again?
                     __syncwarp();
@@ -669,6 +686,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
                 }
+                if (e.c_f16) { store_row_f16(e, g.M, g.N, row, col0, v); continue; }
                 uint8_t* buf = stg0 + sbuf * 4096;
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
@@ -875,7 +893,11 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
         if (sscanf(dbg, "%u,%u", &a, &b) == 2) { g.mn_lbo = a; g.mn_sbo = b; }
     }
     g.tma_store = ((epi.ldc % 4) == 0) && ((((uintptr_t)epi.C) & 15) == 0);
-    if (g.tma_store) {
+    if (epi.c_f16) {
+        PD_REQUIRE(h, !epi.accumulate, "pd_gemm: fp16 output cannot accumulate");
+        g.tma_store = 1;                                   // the register epilogue path; rows go out with vector stores, no TMA
+        tmC = tmA;
+    } else if (g.tma_store) {
         rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     } else {
@@ -887,7 +909,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     // Skinny-M layers (the per-timestep RSSM GEMMs, M = B*I = 50) have too few output tiles to pull their
     // weights through more than a handful of SMs: split K over the idle SMs.  C is zeroed, every split adds its
     // partial product with red.global.add, split 0 also adds bias + residual.
-    if (!epi.accumulate && g.num_m == 1 && epi.act == PD_ACT_NONE && !epi.round_out && tiles * 2 <= h->num_sms &&
+    if (!epi.accumulate && !epi.c_f16 && g.num_m == 1 && epi.act == PD_ACT_NONE && !epi.round_out && tiles * 2 <= h->num_sms &&
         g.kb_total >= 8) {
         int want = h->num_sms / tiles;
         if (const char* ms = getenv("PD_GEMM_SKINNY_MAXSPLIT")) { int v = atoi(ms); if (want > v) want = v; }   // tuning aid

@@ -432,6 +432,9 @@ class Dreamer(nn.Module):
     # forward-only layers (imagination rollout, heads on dreamed features) use fp16 tensor-core operands: the same
     # 10-bit mantissa as TF32 at twice the MMA rate and half the operand traffic; no gradient flows through them.
     fp16_forward = os.environ.get("PD_B200_FP16_FORWARD", "1") != "0"
+    # The decoder's deconvolution column matrices (GEMM output -> col2im fold; written once, read once, ~4 GB per step in fp32)
+    # are stored in fp16 on the fp16-forward product path: half the HBM traffic of the two kernels either side of them.
+    fp16_cols = os.environ.get("PD_B200_FP16_COLS", "1") != "0"
     # conv / deconv contractions gather their operand with TMA im2col-mode loads (pd_conv_gemm) instead of materialising
     # im2col matrices: encoder layers 2-4 (forward + weight gradient), deconv layers 2-3 (input + weight gradient).
     implicit_conv = os.environ.get("PD_B200_IMPLICIT_CONV", "1") != "0"
@@ -1098,7 +1101,7 @@ class Dreamer(nn.Module):
         dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
         xin = x0
         for li, (hi, ho, k, ci, co) in enumerate(dgeo):
-            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co)
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co, dtype=torch.float16 if (self.fp16_forward and self.fp16_cols) else torch.float32)
             ops.gemm(xin, self._decw[li], cols)
             bias = self._raw(dec[2 + 2 * li].bias)
             if li < 3:
@@ -1498,7 +1501,7 @@ class Dreamer(nn.Module):
         dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
         xin = x0
         for li, (hi, ho, k, ci, co) in enumerate(dgeo):
-            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co)
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co, dtype=torch.float16 if (self.fp16_forward and self.fp16_cols) else torch.float32)
             ops.gemm(xin, self._decw[li], cols)
             bias = self._raw(dec[2 + 2 * li].bias)
             if li < 3:

@@ -111,9 +111,10 @@ class NativeOps:
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        flags = (1 if c_zeroed else 0) | (2 if C.dtype == torch.float16 else 0)       # PD_GEMM_C_ZEROED | PD_GEMM_C_F16
         rc = self.lib.pd_gemm(self.h, M, N, K, _ptr(A), _ld(A), int(a_mn), _ptr(B), _ld(B), int(b_mn),
                               _ptr(C), _ld(C), _ptr(bias), _ptr(res), _ld(res) if res is not None else 0,
-                              int(r_div), int(act), int(round_out), int(accumulate), 1 if c_zeroed else 0, self._s())
+                              int(r_div), int(act), int(round_out), int(accumulate), flags, self._s())
         self._ck(rc, "pd_gemm")
         if prof is not None:
             e1.record()
@@ -257,13 +258,14 @@ class NativeOps:
         """out: 4-D view indexed [n, y, x, c]; col: [NB*Hin*Win, k*k*C]."""
         NB, Hout, Wout, Cc = out.shape
         sN, sY, sX, sC = out.stride()
-        self._ck(self.lib.pd_col2im(self.h, NB, Hin, Win, Hout, Wout, Cc, k, _ptr(col), _ld(col), _ptr(bias), int(act),
-                                    int(round_out), _ptr(out), sN, sY, sX, sC, self._s()), "pd_col2im")
+        self._ck(self.lib.pd_col2im_t(self.h, NB, Hin, Win, Hout, Wout, Cc, k, _ptr(col), _ld(col),
+                                      int(col.dtype == torch.float16), _ptr(bias), int(act), int(round_out), _ptr(out), sN, sY,
+                                      sX, sC, self._s()), "pd_col2im")
 
     def col2im_imgloss(self, col, NB, Hin, Win, Cc, k, bias, target, tgt_div, dec, diff, loss, csum):
-        self._ck(self.lib.pd_col2im_imgloss(self.h, NB, Hin, Win, Cc, k, _ptr(col), _ld(col), _ptr(bias), _ptr(target),
-                                            int(tgt_div), _ptr(dec), _ptr(diff), _ptr(loss), _ptr(csum), self._s()),
-                 "pd_col2im_imgloss")
+        self._ck(self.lib.pd_col2im_imgloss_t(self.h, NB, Hin, Win, Cc, k, _ptr(col), _ld(col),
+                                              int(col.dtype == torch.float16), _ptr(bias), _ptr(target), int(tgt_div),
+                                              _ptr(dec), _ptr(diff), _ptr(loss), _ptr(csum), self._s()), "pd_col2im_imgloss")
 
     def bias_act_bwd(self, dy, y, act, db):
         M, N = dy.shape

@@ -485,3 +485,39 @@ def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
     assert torch.equal(C2, C2r), f"mode 2 max diff {(C2 - C2r).abs().max().item()}"
     ops.conv_gemm(3, X, k, Ot, C3); ref.conv_gemm(3, X, k, Ot, C3r)
     assert torch.equal(C3, C3r), f"mode 3 max diff {(C3 - C3r).abs().max().item()}"
+
+
+@pytest.mark.parametrize("NB,Hin,k,Cc", [(3, 5, 5, 16), (2, 13, 6, 48), (5, 4, 6, 4)])
+def test_fp16_column_matrix_gemm_store_and_col2im(ops, ref, NB, Hin, k, Cc):
+    """Decoder forward with fp16 column matrices: pd_gemm writes C as fp16 (PD_GEMM_C_F16) and pd_col2im / pd_col2im_imgloss
+    fold it back.  Integer-valued operands keep every product and sum exact in fp16, so the native path must equal the twin
+    bit for bit; random operands stay within one fp16 rounding of the fp32-column result."""
+    Cin = 24
+    rows = NB * Hin * Hin
+    X, Wt = ints(rows, Cin, lo=-2, hi=3), ints(k * k * Cc, Cin, seed=1, lo=-2, hi=3)
+    Hout = (Hin - 1) * 2 + k
+    bias = ints(Cc, seed=2)
+    got = {}
+    for name, o in (("n", ops), ("r", ref)):
+        cols = torch.zeros(rows, k * k * Cc, device=DEV, dtype=torch.float16)
+        o.gemm(X, Wt, cols)
+        out = torch.zeros(NB, Hout, Hout, Cc, device=DEV)
+        o.col2im(cols, Hin, Hin, k, bias, 1, out, round_out=False)
+        got[name] = (cols.clone(), out)
+    assert torch.equal(got["n"][0], got["r"][0]), "fp16 GEMM output"
+    close(got["n"][1], got["r"][1], 1e-6, 1e-6, "col2im over fp16 columns")
+    # random operands against the fp32-column path
+    Xr, Wr = rnd(rows, Cin), rnd(k * k * Cc, Cin, seed=1) * 0.2
+    c16, c32 = torch.zeros(rows, k * k * Cc, device=DEV, dtype=torch.float16), torch.zeros(rows, k * k * Cc, device=DEV)
+    ops.gemm(Xr, Wr, c16); ops.gemm(Xr, Wr, c32)
+    close(c16.float(), c32, 1e-3, 1e-4, "fp16 vs fp32 columns")
+    if Cc <= 16:                                            # the fused last-layer fold + image loss over fp16 columns
+        tgt = rnd(NB, Cc, Hout, Hout, seed=5)
+        res = {}
+        for name, o in (("n", ops), ("r", ref)):
+            dec, diff = torch.zeros(NB, Cc, Hout, Hout, device=DEV), torch.zeros(NB, Cc, Hout, Hout, device=DEV)
+            loss, csum = torch.zeros(NB, device=DEV), torch.zeros(NB, Cc, device=DEV)
+            o.col2im_imgloss(c16, NB, Hin, Hin, Cc, k, bias, tgt, 1, dec, diff, loss, csum)
+            res[name] = (dec, diff, loss, csum)
+        for a, b_, w in zip(res["n"], res["r"], ("dec", "diff", "loss", "csum")):
+            close(a, b_, 2e-5, 1e-5, "imgloss over fp16 columns: " + w)
