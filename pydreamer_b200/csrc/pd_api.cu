@@ -75,7 +75,8 @@ int pd_gemm(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_m
     // Skinny / unaligned contractions (scalar heads N=1, action inputs K=18, ...) cannot be described
     // by a TMA tensor map (16-byte strides) and have no tensor-core work to speak of: CUDA cores.
     const bool tma_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) &&
-                        ((((uintptr_t)B) & 15) == 0) && N >= 8 && K >= 8;
+                        ((((uintptr_t)B) & 15) == 0) && N >= 8 && K >= 8 &&
+                        (!e.c_f16 || ((ldc % 8 == 0) && !R && !round_out && ((((uintptr_t)C) & 15) == 0)));
     if (h->gemm_impl == PD_GEMM_SIMT || !tma_ok)
         return pd_gemm_simt_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream);
     return pd_gemm_tcgen05_launch(h, M, N, K, A, lda, a_mn, B, ldb, b_mn, e, (cudaStream_t)stream, 0);

@@ -150,18 +150,50 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// fp16 output: thread = one row x 32 consecutive columns of the tile; rows of C are written as 64-byte runs
-__device__ __forceinline__ void store_row_f16(const PdEpilogue& e, int M, int N, int row, int col0, const float (&v)[32]) {
-    if (row >= M) return;
-    __half* dst = reinterpret_cast<__half*>(e.C) + (long)row * e.ldc + col0;
-    if (col0 + 32 <= N && (e.ldc & 3) == 0 && (((uintptr_t)e.C) & 7) == 0) {
+// fp16 output (PD_GEMM_C_F16): one epilogue warp converts PAIRS of 32-column chunks (64 halfs = one 128-byte row per thread),
+// stages them in the same 128B-swizzled 32-row box the fp32 path uses and hands the box to the copy engine (tensor map over
+// the fp16 matrix, box {64 halfs, 32 rows}).  Called warp-uniformly; `chalf` selects this warp's pairs.
+__device__ __forceinline__ void epi_f16_tile(const PdEpilogue& e, const CUtensorMap* tmC, int N, uint32_t tbase, int n0, int rbase,
+                                             int nchunk, int chalf, bool extras, uint8_t* stg0, int& sbuf) {
+    const int lane = threadIdx.x & 31;
+    const int npair = (nchunk + 1) >> 1;
+#pragma unroll 1
+    for (int cp = chalf; cp < npair; cp += 2) {
+        __half2 h[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            __half2 h2[2] = {__floats2half2_rn(v[4 * j], v[4 * j + 1]), __floats2half2_rn(v[4 * j + 2], v[4 * j + 3])};
-            *reinterpret_cast<uint2*>(dst + 4 * j) = *reinterpret_cast<const uint2*>(h2);
+        for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tc_ld_32x32b_x32(tbase + (uint32_t)(cp * 64 + hh * 32), r);
+            const int col0 = n0 + cp * 64 + hh * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
+                if (extras && e.bias) {
+                    x0 += (col0 + j < N) ? __ldg(e.bias + col0 + j) : 0.f;
+                    x1 += (col0 + j + 1 < N) ? __ldg(e.bias + col0 + j + 1) : 0.f;
+                }
+                if (e.act == PD_ACT_ELU) { x0 = pd_elu(x0); x1 = pd_elu(x1); }
+                h[hh * 16 + (j >> 1)] = __floats2half2_rn(x0, x1);
+            }
         }
-    } else {
-        for (int j = 0; j < 32; ++j) if (col0 + j < N) dst[j] = __float2half_rn(v[j]);
+        uint8_t* buf = stg0 + sbuf * 4096;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t rowaddr = smem_u32(buf) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                         // SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7)
+            const uint4 q = *reinterpret_cast<const uint4*>(&h[4 * j]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4)), "r"(q.x),
+                         "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"((uint64_t)tmC), "r"(smem_u32(buf)), "r"(n0 + cp * 64), "r"(rbase) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        sbuf ^= 1;
     }
 }
 
@@ -336,8 +368,9 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
             const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
             const int nchunk = rbase >= g.M ? 0 : min(BN / 32, (g.N - n0 + 31) / 32);   // chunks with real columns (warp-uniform)
+            if (e.c_f16) epi_f16_tile(e, &tmC, g.N, tbase, n0, rbase, nchunk, chalf, extras, stg0, sbuf);
 #pragma unroll 1
-            for (int c = chalf; c < nchunk; c += 2) {
+            for (int c = chalf; c < (e.c_f16 ? 0 : nchunk); c += 2) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);     // warp-collective: no divergence above
                 const int col0 = n0 + c * 32;
@@ -380,7 +413,6 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
                     }
-                    if (e.c_f16) { store_row_f16(e, g.M, g.N, row, col0, v); continue; }
                     uint8_t* buf = stg0 + sbuf * 4096;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer free again?
                     __syncwarp();
@@ -643,8 +675,9 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t tbase = tmem_base + (uint32_t)(as * BN2) + ((uint32_t)(quarter * 32) << 16);
             const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
             const int nchunk = rbase >= g.M ? 0 : min(BN2 / 32, (g.N - n0 + 31) / 32);
+            if (e.c_f16) epi_f16_tile(e, &tmC, g.N, tbase, n0, rbase, nchunk, chalf, extras, stg0, sbuf);
 #pragma unroll 1
-            for (int c = chalf; c < nchunk; c += 2) {
+            for (int c = chalf; c < (e.c_f16 ? 0 : nchunk); c += 2) {
                 uint32_t r[32];
                 tc_ld_32x32b_x32(tbase + (uint32_t)(c * 32), r);
                 const int col0 = n0 + c * 32;
@@ -686,7 +719,6 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
                 }
-                if (e.c_f16) { store_row_f16(e, g.M, g.N, row, col0, v); continue; }
                 uint8_t* buf = stg0 + sbuf * 4096;
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
@@ -894,9 +926,11 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     }
     g.tma_store = ((epi.ldc % 4) == 0) && ((((uintptr_t)epi.C) & 15) == 0);
     if (epi.c_f16) {
-        PD_REQUIRE(h, !epi.accumulate, "pd_gemm: fp16 output cannot accumulate");
-        g.tma_store = 1;                                   // the register epilogue path; rows go out with vector stores, no TMA
-        tmC = tmA;
+        PD_REQUIRE(h, !epi.accumulate && !epi.R && !epi.round_out, "pd_gemm: an fp16 output takes bias / activation only");
+        PD_REQUIRE(h, (epi.ldc % 8) == 0 && ((((uintptr_t)epi.C) & 15) == 0), "pd_gemm: fp16 output needs ldc %% 8 == 0 (16-byte rows)");
+        g.tma_store = 1;
+        rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, 2);
+        if (rc) return rc;
     } else if (g.tma_store) {
         rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;

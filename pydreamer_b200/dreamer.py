@@ -434,7 +434,7 @@ class Dreamer(nn.Module):
     fp16_forward = os.environ.get("PD_B200_FP16_FORWARD", "1") != "0"
     # The decoder's deconvolution column matrices (GEMM output -> col2im fold; written once, read once, ~4 GB per step in fp32)
     # are stored in fp16 on the fp16-forward product path: half the HBM traffic of the two kernels either side of them.
-    fp16_cols = os.environ.get("PD_B200_FP16_COLS", "1") != "0"
+    fp16_cols = os.environ.get("PD_B200_FP16_COLS", "0") != "0"
     # conv / deconv contractions gather their operand with TMA im2col-mode loads (pd_conv_gemm) instead of materialising
     # im2col matrices: encoder layers 2-4 (forward + weight gradient), deconv layers 2-3 (input + weight gradient).
     implicit_conv = os.environ.get("PD_B200_IMPLICIT_CONV", "1") != "0"
@@ -1087,6 +1087,11 @@ class Dreamer(nn.Module):
         tensors.update(logprob_image=lp_img, logprob_reward=lp_rew, logprob_terminal=lp_term, **extra_t,
                        image_pred=sel(dd["image"]), reward_pred=sel(dd["rec_r"]), terminal_pred=sel(dd["rec_t"]))
 
+    def _cols_dtype(self, ncols):
+        """Column matrices of the transposed convolutions are written once and read once: fp16 halves that traffic.  The GEMM's
+        fp16 TMA store needs 16-byte rows (ncols % 8 == 0); the last layer (k*k*3 columns) stays fp32."""
+        return torch.float16 if (self.fp16_forward and self.fp16_cols and ncols % 8 == 0) else torch.float32
+
     def _decode_all(self, featN, img, obs, N, NB, I, tag):
         """MultiDecoder.training_step forward (decoders.py:50-108) on features (N,F): image decoder (Linear, then each
         deconv = GEMM + col2im gather with bias+ELU; the last one fused with the image loss) and the reward / terminal
@@ -1101,7 +1106,7 @@ class Dreamer(nn.Module):
         dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
         xin = x0
         for li, (hi, ho, k, ci, co) in enumerate(dgeo):
-            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co, dtype=torch.float16 if (self.fp16_forward and self.fp16_cols) else torch.float32)
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co, dtype=self._cols_dtype(k * k * co))
             ops.gemm(xin, self._decw[li], cols)
             bias = self._raw(dec[2 + 2 * li].bias)
             if li < 3:
@@ -1501,7 +1506,7 @@ class Dreamer(nn.Module):
         dgeo = ((1, 5, 5, 32 * cd, 4 * cd), (5, 13, 5, 4 * cd, 2 * cd), (13, 30, 6, 2 * cd, cd), (30, 64, 6, cd, IC))
         xin = x0
         for li, (hi, ho, k, ci, co) in enumerate(dgeo):
-            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co, dtype=torch.float16 if (self.fp16_forward and self.fp16_cols) else torch.float32)
+            cols = b(f"dec.cols{li}", N * hi * hi, k * k * co, dtype=self._cols_dtype(k * k * co))
             ops.gemm(xin, self._decw[li], cols)
             bias = self._raw(dec[2 + 2 * li].bias)
             if li < 3:
