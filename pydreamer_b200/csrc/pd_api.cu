@@ -31,6 +31,10 @@ int pd_create(int device_ordinal, pd_handle** out) {
     h->round_ops = 1;
     h->gemm_2cta = 1;
     if (const char* e2 = getenv("PD_GEMM_2CTA")) h->gemm_2cta = atoi(e2);
+    h->gemm_mn3 = 1;
+    h->gemm_conv_k64 = 1;
+    if (const char* e4 = getenv("PD_GEMM_CONV_K64")) h->gemm_conv_k64 = atoi(e4);
+    if (const char* e3 = getenv("PD_GEMM_MN3")) h->gemm_mn3 = atoi(e3);
     cudaSetDevice(device_ordinal);
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;

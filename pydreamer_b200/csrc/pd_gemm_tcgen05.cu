@@ -44,6 +44,10 @@ struct GemmArgs {
     int a_mn, b_mn;
     int num_m, num_n, splits, kb_total, kb_per_split;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
+    // MN-major tiled operands: one 3-D box {32 columns, 32 k-rows, 4 column groups} (16 KB) instead of four 2-D boxes of 4 KB
+    // (tools/microbench/tma_box_rate.cu: 4 KB boxes stream at 9.9 B/clk/SM, 16 KB boxes at 25).  a3_on / b3_on: the 3-D map is
+    // valid; a3_part / b3_part: index of the one partial column group (MN % 32 != 0; tiles holding it keep the 2-D boxes), or -1.
+    int a3_on, b3_on, a3_part, b3_part;
     // implicit-GEMM convolution operands (TMA im2col mode on an NHWC tensor, k x k taps, stride 2, no padding):
     //   a_mode 1: A rows = output pixels, K = (tap, channel)            (conv forward / deconv input-gradient)
     //   a_mode 2: A' rows = (tap, channel padded to 32), K = output pixels  (deconv weight gradient)
@@ -91,6 +95,14 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
         ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// MN-major tile whose first column group is gi: may it be fetched as one 3-D box (no partial column group inside)?
+__device__ __forceinline__ bool mn3_ok(int on, int part, int gi) { return on && !(part >= gi && part < gi + 4); }
 __device__ __forceinline__ void tma_load_im2col(const void* tmap, uint64_t* bar, void* smem, int c, int w, int h, int n,
                                                 int off_w, int off_h) {
     asm volatile(
@@ -197,10 +209,23 @@ __device__ __forceinline__ void epi_f16_tile(const PdEpilogue& e, const CUtensor
     }
 }
 
+// BIG: the instantiation for pd_conv_gemm modes 2 / 3 (K = output pixels, both operands MN-major): k-blocks of 64 pixels
+// (three 64 KB stages, one 4 KB store box per epilogue warp) so that the im2col operand arrives as four 8 KB boxes per
+// 64 pixels instead of eight 4 KB boxes — its TMA boxes cost ~415 clk each whatever their size up to 8 KB
+// (tools/microbench/tma_box_rate.cu; the r02 ncu of mode 2 showed exactly 4 x 415 clk per k-block).
+template <bool BIG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA3,
+                    const __grid_constant__ CUtensorMap tmB3, const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int NST = BIG ? 3 : STAGES;                       // NST * STB + staging = STAGES * STAGE_BYTES + EPI_STAGING
+    constexpr int STB = BIG ? 2 * STAGE_BYTES : STAGE_BYTES;
+    constexpr int ABY = BIG ? 2 * A_BYTES : A_BYTES;
+    constexpr int KSTEPS = (BIG ? 2 : 1) * (BK / UMMA_K);
+    constexpr int GSTR = BIG ? 8192 : 4096;                     // bytes between the 32-column groups of an MN-major operand
+    constexpr int KROWS = BIG ? 64 : 32;                        // k-rows (pixels) of one MN-major k-block
+    static_assert(NST * STB + EPI_WARPS * (BIG ? 1 : 2) * 4096 == STAGES * STAGE_BYTES + EPI_STAGING, "same shared-memory footprint");
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_STAGING);
@@ -216,6 +241,8 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        if (g.a3_on) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+        if (g.b3_on) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB3) : "memory");
         if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
@@ -247,10 +274,10 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    int k0 = kb * (g.f16 ? 2 * BK : BK);
+                    uint8_t* sa = smem + stage * STB;
+                    uint8_t* sb = sa + ABY;
+                    mbar_expect_tx(&full[stage], STB);
+                    int k0 = kb * ((g.f16 || BIG) ? 2 * BK : BK);
                     if (g.a_mode == 1) {
                         // implicit im2col rows: k-block = 32 channels of one filter tap; pixel tile starts at m0
                         const int tap = kb / g.cv_cblocks, c0 = (kb - tap * g.cv_cblocks) * 32;
@@ -264,7 +291,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     if (g.a_mode == 2 || g.b_mode == 2) {
                         // K = output pixels: k-block = 32 consecutive pixels starting at kb*32
-                        const int pix = kb * 32;
+                        const int pix = kb * KROWS;
                         const int n_ = pix / g.cv_PQ, r_ = pix - n_ * g.cv_PQ;
                         const int p_ = r_ / g.cv_Q, q_ = r_ - p_ * g.cv_Q;
                         const void* tm = g.a_mode == 2 ? (const void*)&tmA : (const void*)&tmB;
@@ -276,28 +303,32 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             int tap = idx / g.cv_cpad, c0 = idx - tap * g.cv_cpad;
                             if (tap >= g.cv_k * g.cv_k) { tap = 0; c0 = g.cv_cpad + 32; }        // past the last tap: all-OOB -> zeros
                             const int kh = tap / g.cv_k, kw = tap - kh * g.cv_k;
-                            tma_load_im2col(tm, &full[stage], dst + j * 4096, c0, 2 * q_, 2 * p_, n_, kw, kh);
+                            tma_load_im2col(tm, &full[stage], dst + j * GSTR, c0, 2 * q_, 2 * p_, n_, kw, kh);
                         }
                     }
                     if (g.a_mode == 0) {
                         if (!g.a_mn) {
                             tma_load_2d(&tmA, &full[stage], sa, k0, m0);              // box {32 k, 128 m}
+                        } else if (mn3_ok(g.a3_on, g.a3_part, m0 >> 5)) {
+                            tma_load_3d(&tmA3, &full[stage], sa, 0, k0, m0 >> 5);     // box {32 m, 32 k, 4 groups}
                         } else {
 #pragma unroll
                             for (int j = 0; j < BM / 32; ++j)                        // box {32 m, 32 k} x 4
-                                tma_load_2d(&tmA, &full[stage], sa + j * 4096, m0 + j * 32, k0);
+                                tma_load_2d(&tmA, &full[stage], sa + j * GSTR, m0 + j * 32, k0);
                         }
                     }
                     if (g.b_mode == 0) {
                         if (!g.b_mn) {
                             tma_load_2d(&tmB, &full[stage], sb, k0, n0);
+                        } else if (mn3_ok(g.b3_on, g.b3_part, n0 >> 5)) {
+                            tma_load_3d(&tmB3, &full[stage], sb, 0, k0, n0 >> 5);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BN / 32; ++j)
-                                tma_load_2d(&tmB, &full[stage], sb + j * 4096, n0 + j * 32, k0);
+                                tma_load_2d(&tmB, &full[stage], sb + j * GSTR, n0 + j * 32, k0);
                         }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -321,10 +352,10 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint32_t sa = smem_u32(smem + stage * STB);
+                    const uint32_t sb = sa + ABY;
 #pragma unroll
-                    for (int s = 0; s < BK / UMMA_K; ++s) {
+                    for (int s = 0; s < KSTEPS; ++s) {
                         // MN-major: 8 k-rows per MMA = two 4-row (512 B) swizzle atoms, SBO apart;
                         //           LBO = 4096 B between 32-element MN groups (one TMA box each).
                         const uint64_t ad = g.a_mn ? make_desc(sa + s * 1024, g.mn_lbo, g.mn_sbo, 1)
@@ -335,7 +366,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         else       tc_mma_tf32(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull[as]);                 // accumulator tile complete
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
@@ -351,7 +382,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int chalf = (warp - 2) >> 2;             // which of the quarter's two warps: chunks chalf, chalf + 2, ...
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
-        uint8_t* stg0 = smem + STAGES * STAGE_BYTES + (warp - 2) * (2 * 4096);
+        uint8_t* stg0 = smem + NST * STB + (warp - 2) * ((BIG ? 1 : 2) * 4096);   // BIG: one store box per warp
         const bool b_vec = e.bias && ((((uintptr_t)e.bias) & 15) == 0);
         float* stgf = reinterpret_cast<float*>(stg0);     // scalar fallback view (pitch 33 floats fits in 8 KB)
         int sbuf = 0;
@@ -414,7 +445,10 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
                     }
                     uint8_t* buf = stg0 + sbuf * 4096;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer free again?
+                    if (lane == 0) {                                                                 // buffer free again?
+                        if (BIG) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        else     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    }
                     __syncwarp();
                     const uint32_t rowaddr = smem_u32(buf) + lane * 128;
 #pragma unroll
@@ -435,7 +469,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                          ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    sbuf ^= 1;
+                    if (!BIG) sbuf ^= 1;
                 } else {
                     // generic fallback (C not TMA-addressable: ldc % 4 != 0, e.g. N = 1 / 18 outputs)
 #pragma unroll
@@ -511,6 +545,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint32_t leade
         ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t leader_bar, void* smem, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {     // arrives on this barrier offset in BOTH CTAs
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -541,7 +581,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA3,
+                         const __grid_constant__ CUtensorMap tmB3, const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + STAGES2 * STAGE2_BYTES + EPI_STAGING);
@@ -559,6 +600,8 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        if (g.a3_on) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+        if (g.b3_on) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB3) : "memory");
         if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
         for (int i = 0; i < STAGES2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * EPI_WARPS); }
@@ -600,12 +643,16 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const int k0 = kb * (g.f16 ? 2 * BK : BK);
                     if (!g.a_mn) {
                         tma_load_2d_2sm(&tmA, lbar, sa, k0, m0);
+                    } else if (mn3_ok(g.a3_on, g.a3_part, m0 >> 5)) {
+                        tma_load_3d_2sm(&tmA3, lbar, sa, 0, k0, m0 >> 5);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 32; ++j) tma_load_2d_2sm(&tmA, lbar, sa + j * 4096, m0 + j * 32, k0);
                     }
                     if (!g.b_mn) {
                         tma_load_2d_2sm(&tmB, lbar, sb, k0, n0);
+                    } else if (BNH == 128 && mn3_ok(g.b3_on, g.b3_part, n0 >> 5)) {
+                        tma_load_3d_2sm(&tmB3, lbar, sb, 0, k0, n0 >> 5);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BNH / 32; ++j) tma_load_2d_2sm(&tmB, lbar, sb + j * 4096, n0 + j * 32, k0);
@@ -779,6 +826,28 @@ int make_map(pd_handle* h, CUtensorMap* tm, const void* base, uint64_t dim0, uin
     return PD_OK;
 }
 
+// 3-D view of an MN-major fp32 operand [K rows][MN columns, ld]: (32 columns of a group, k, column group) with strides
+// (ld * 4 B, 128 B), box {32, 32, 4} — in shared memory the same bytes as four 2-D {32, 32} boxes 4096 B apart.  Only the
+// MN / 32 FULL column groups are addressable (a partial last group would read past the row); *on = 0 if there is none.
+int make_map3(pd_handle* h, CUtensorMap* tm, const void* base, uint64_t mn, uint64_t k, uint64_t ld_elems, int* on, int* part,
+              int krows = BK) {
+    const uint64_t groups = mn / 32;
+    *part = (mn % 32) ? (int)groups : -1;
+    *on = 0;
+    if (groups == 0) return PD_OK;
+    cuuint64_t gdim[3] = {32, k, groups};
+    cuuint64_t gstride[2] = {ld_elems * 4, 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)krows, 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "cuTensorMapEncodeTiled(3-D MN-major) failed (%d): mn %llu k %llu ld %llu", (int)r,
+                                   (unsigned long long)mn, (unsigned long long)k, (unsigned long long)ld_elems);
+    *on = 1;
+    return PD_OK;
+}
+
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -838,7 +907,8 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     PD_REQUIRE(h, (ldo % 4) == 0 && ((((uintptr_t)O) & 15) == 0), "pd_conv_gemm: operand alignment");
     PD_REQUIRE(h, (epi.ldc % 4) == 0 && ((((uintptr_t)epi.C) & 15) == 0), "pd_conv_gemm: C must be TMA-addressable");
     if (!h->gemm_smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
         h->gemm_smem_configured = 1;
     }
@@ -847,9 +917,14 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.cv_PQ = P * Q; g.cv_Q = Q; g.cv_C = C; g.cv_k = k; g.cv_cblocks = pd_cdiv(C, 32); g.cv_cpad = g.cv_cblocks * 32;
-    g.mn_lbo = 4096; g.mn_sbo = 512;
+    // modes 2 / 3 (K = pixels): 64-pixel k-blocks, the BIG instantiation (PD_GEMM_CONV_K64=0: the 32-pixel form)
+    const bool big = mode != 1 && h->gemm_conv_k64;
+    const int kpix = big ? 64 : 32;
+    g.mn_lbo = big ? 8192 : 4096; g.mn_sbo = 512;
     g.epi = epi; g.tma_store = 1;
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmA3, tmB3;
+    memset(&tmA3, 0, sizeof(tmA3)); memset(&tmB3, 0, sizeof(tmB3));
+    g.a3_part = g.b3_part = -1;
     int rc, M, N;
     if (mode == 1) {
         M = (int)pixels; N = ODIM;
@@ -863,29 +938,32 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     } else if (mode == 2) {
         M = k * k * g.cv_cpad; N = ODIM;
         g.a_mode = 2; g.a_mn = 1; g.b_mode = 0; g.b_mn = 1;
-        g.kb_total = pd_cdiv(pixels, 32);
-        rc = make_im2col_map(h, &tmA, X, NB, H, W, C, k, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
-        rc = make_map(h, &tmB, O, (uint64_t)N, (uint64_t)pixels, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        g.kb_total = pd_cdiv(pixels, kpix);
+        rc = make_im2col_map(h, &tmA, X, NB, H, W, C, k, kpix, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
+        rc = make_map(h, &tmB, O, (uint64_t)N, (uint64_t)pixels, (uint64_t)ldo, 32, kpix, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
+        if (h->gemm_mn3) { rc = make_map3(h, &tmB3, O, (uint64_t)N, (uint64_t)pixels, (uint64_t)ldo, &g.b3_on, &g.b3_part, kpix); if (rc) return rc; }
     } else {
         M = ODIM; N = k * k * g.cv_cpad;
         g.a_mode = 0; g.a_mn = 1; g.b_mode = 2; g.b_mn = 1;
-        g.kb_total = pd_cdiv(pixels, 32);
-        rc = make_map(h, &tmA, O, (uint64_t)M, (uint64_t)pixels, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        g.kb_total = pd_cdiv(pixels, kpix);
+        rc = make_map(h, &tmA, O, (uint64_t)M, (uint64_t)pixels, (uint64_t)ldo, 32, kpix, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
-        rc = make_im2col_map(h, &tmB, X, NB, H, W, C, k, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
+        if (h->gemm_mn3) { rc = make_map3(h, &tmA3, O, (uint64_t)M, (uint64_t)pixels, (uint64_t)ldo, &g.a3_on, &g.a3_part, kpix); if (rc) return rc; }
+        rc = make_im2col_map(h, &tmB, X, NB, H, W, C, k, kpix, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
     }
     rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     g.M = M; g.N = N; g.K = 0;
     g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
     int tiles = g.num_m * g.num_n, splits = 1;
-    if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, 8);
+    if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, big ? 4 : 8);
     g.kb_per_split = pd_cdiv(g.kb_total, splits);
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
     int units = tiles * g.splits;
     int grid = units < h->num_sms ? units : h->num_sms;
-    pd_gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
+    if (big) pd_gemm_tf32_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    else     pd_gemm_tf32_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel(im2col)");
     return PD_OK;
 }
@@ -897,11 +975,13 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
                lda, ldb);
     PD_REQUIRE(h, (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "pd_gemm(tcgen05): A/B must be 16B aligned");
     if (!h->gemm_smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
         h->gemm_smem_configured = 1;
     }
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmA3, tmB3;
+    memset(&tmA3, 0, sizeof(tmA3)); memset(&tmB3, 0, sizeof(tmB3));
     int rc;
     if (f16)        rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 2 * BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, 2);
     else if (!a_mn) rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -920,6 +1000,9 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     g.kb_total = pd_cdiv(K, f16 ? 2 * BK : BK);
     g.epi = epi;
     g.mn_lbo = 4096; g.mn_sbo = 512;
+    g.a3_part = g.b3_part = -1;
+    if (h->gemm_mn3 && !f16 && a_mn) { rc = make_map3(h, &tmA3, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, &g.a3_on, &g.a3_part); if (rc) return rc; }
+    if (h->gemm_mn3 && !f16 && b_mn) { rc = make_map3(h, &tmB3, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, &g.b3_on, &g.b3_part); if (rc) return rc; }
     if (const char* dbg = getenv("PD_GEMM_MN_DESC")) {   // bring-up aid: "lbo,sbo" in bytes
         unsigned a = 0, b = 0;
         if (sscanf(dbg, "%u,%u", &a, &b) == 2) { g.mn_lbo = a; g.mn_sbo = b; }
@@ -981,7 +1064,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
                 if (e2 != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(2cta smem=%d): %s", SMEM2_BYTES, cudaGetErrorString(e2));
                 h->gemm2_smem_configured = 1;
             }
-            pd_gemm_tf32_2cta_kernel<<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, g);
+            pd_gemm_tf32_2cta_kernel<<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
             PD_CHECK_LAUNCH(h, "pd_gemm_tf32_2cta_kernel");
             return PD_OK;
         }
@@ -990,7 +1073,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units
     int units = tiles * g.splits;
     int grid = units < h->num_sms ? units : h->num_sms;
-    pd_gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
+    pd_gemm_tf32_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel");
     return PD_OK;
 }

@@ -173,7 +173,7 @@ __device__ __forceinline__ uint32_t job_bytes(const Job<MAXT>& j, int kb) {
 // Producer: weights of the first stages are requested before the grid barrier `wait_epoch` (0 = nothing to wait for),
 // activation boxes after it.
 template <int MAXT, int XB>
-__device__ void produce(Ring<MAXT, XB>& ring, const Job<MAXT>& j, const unsigned* ctr, unsigned wait_epoch) {
+__device__ void produce(Ring<MAXT, XB>& ring, const Job<MAXT>& j, const unsigned* ctr, unsigned wait_epoch, int xrow_off = 0) {
     const int npre = j.nkb < NSTAGE ? j.nkb : NSTAGE;
     auto weights = [&](int kb) {
         const uint32_t n = ring.n + kb;
@@ -188,15 +188,16 @@ __device__ void produce(Ring<MAXT, XB>& ring, const Job<MAXT>& j, const unsigned
         uint64_t* bar = ring.full + n % NSTAGE;
         const int kf = j.kcol0 + kb * KB;                           // contraction index of this k-block
         const bool x2 = job_needs_x2(j, kb);
+        const int xr = j.xrow0 + xrow_off;                          // xrow_off: the same job over another block of batch rows
         if (j.xf16) {
-            tma_box(j.xmap[0], bar, st, kf, j.xrow0);
-            if (x2) tma_box(j.xmap[1], bar, st + X_BOX, kf, j.xrow0);
+            tma_box(j.xmap[0], bar, st, kf, xr);
+            if (x2) tma_box(j.xmap[1], bar, st + X_BOX, kf, xr);
         } else {
-            tma_box(j.xmap[0], bar, st, kf, j.xrow0);
-            tma_box(j.xmap[0], bar, st + X_BOX, kf + 32, j.xrow0);
+            tma_box(j.xmap[0], bar, st, kf, xr);
+            tma_box(j.xmap[0], bar, st + X_BOX, kf + 32, xr);
             if (x2) {
-                tma_box(j.xmap[1], bar, st + 2 * X_BOX, kf, j.xrow0);
-                tma_box(j.xmap[1], bar, st + 3 * X_BOX, kf + 32, j.xrow0);
+                tma_box(j.xmap[1], bar, st + 2 * X_BOX, kf, xr);
+                tma_box(j.xmap[1], bar, st + 3 * X_BOX, kf + 32, xr);
             }
         }
     };
@@ -360,7 +361,8 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(int N) { return (1u << 4) | (
 // (accumulators at TMEM columns tmem + ut * NCOL) and commits the stage; after the last stage it commits `accbar`, which every
 // consumer thread then waits for (parity `accpar`) before reading TMEM.
 template <int NUT, int NCOL, int MAXT, int XB>
-__device__ void consume_umma(Ring<MAXT, XB>& ring, const Job<MAXT>& j, uint32_t tmem, uint64_t* accbar, uint32_t accpar) {
+__device__ void consume_umma(Ring<MAXT, XB>& ring, const Job<MAXT>& j, uint32_t tmem, uint64_t* accbar, uint32_t accpar,
+                             bool finish = true) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idesc = umma_idesc_f16(NCOL);
     for (int kb = 0; kb < j.nkb; ++kb) {
@@ -379,7 +381,8 @@ __device__ void consume_umma(Ring<MAXT, XB>& ring, const Job<MAXT>& j, uint32_t 
                                    (kb > 0 || ks > 0) ? 1u : 0u);
                 }
                 tc_commit(ring.empty + n % NSTAGE);                 // one arrival when these MMAs have retired
-                if (kb == j.nkb - 1) tc_commit(accbar);
+                if (finish && kb == j.nkb - 1) tc_commit(accbar);   // (finish = false: more MMAs of this phase follow, into
+                                                                    //  other TMEM columns; the last job's commit covers them all)
             }
             __syncwarp();
         } else {
@@ -387,7 +390,7 @@ __device__ void consume_umma(Ring<MAXT, XB>& ring, const Job<MAXT>& j, uint32_t 
         }
     }
     ring.n += j.nkb;
-    if (j.nkb > 0) {
+    if (finish && j.nkb > 0) {
         mbar_wait(accbar, accpar);
         tc_fence_after();
     }

@@ -20,6 +20,12 @@
 // 16-row TMA boxes form one UMMA A tile), N = 64 batch rows, accumulators in TMEM, read back with tcgen05.ld for the
 // epilogues (r02 phase clocks of the mma.sync version: phase C spent 8.6 of its 11.4 us issuing legacy HMMA).  The small
 // logits contraction of phase D (32 rows x 16 batch rows) stays on mma.sync.
+//
+// Batch rows beyond one 64-row MMA operand (IWAE: BI = B x iwae_samples, world.py:60-68 repeats every sequence I times) run in
+// the MULTI instantiation: phases B and C repeat their contraction per block of 64 rows into separate TMEM columns (all
+// blocks' MMAs are issued back to back, one commit, then the epilogues block by block), phase D takes 64 rows per pass with
+// all eight warps, and the row owners of A / C' stride over the rows by the grid size.  The single-block instantiation is
+// the round-2 kernel unchanged (same-box A/B: a run-time block loop around its phases cost 0.38 ms on the Atari shape).
 #include "pd_k1_pipe.cuh"
 
 namespace {
@@ -32,19 +38,21 @@ typedef Job<MAXT> JobF;
 constexpr int OFF_BAR = RingF::BYTES;
 constexpr int OFF_SH = OFF_BAR + 128;                       // 64 floats: block reductions
 constexpr int OFF_SIDX = OFF_SH + 256;                      // 64 ints: sampled classes of one row
-constexpr int OFF_HC = OFF_SIDX + 256;                      // [16][BROWS] floats: masked h of my units (input of the next step)
-constexpr int OFF_PART = OFF_HC + 16 * BROWS * 4;           // [2][1024] floats: phase A gather halves
-constexpr int OFF_LOG = OFF_PART + 2 * 1024 * 4;            // [16][32] floats: phase D logits of my rows
-constexpr int OFF_GI = OFF_LOG + 16 * 32 * 4;               // [48][65] floats: phase B gi of my units (from TMEM, for the gate math)
+constexpr int HB = 256;                                     // batch rows the MULTI instantiation takes (4 blocks of BROWS)
+constexpr int OFF_HC = OFF_SIDX + 256;                      // [16][BROWS or HB] floats: masked h of my units (input of the next step)
+constexpr int OFF_PART = OFF_HC + 16 * HB * 4;              // [2][1024] floats: phase A gather halves
+constexpr int OFF_LOG = OFF_PART + 2 * 1024 * 4;            // [16 or 64][32] floats: phase D logits of my rows
+constexpr int OFF_GI = OFF_LOG + 64 * 32 * 4;               // [48][65] floats: phase B gi of my units (from TMEM, for the gate math)
 constexpr int OFF_TM = OFF_GI + 48 * 65 * 4;                // accumulator-ready mbarrier (8 B) + TMEM base address (4 B)
 constexpr int SMEM_BYTES = OFF_TM + 64;
-constexpr int TMEM_COLS = 128;                              // two UMMA tiles x 64 batch columns
+// TMEM columns: two UMMA tiles x 64 batch columns per block of batch rows (128, or all 512 with four blocks)
 constexpr int KSPLIT = 4;
 
 struct FwdMaps {
     CUtensorMap wih, whh, wph, wpm;            // fp16 weights, box {64 halfs, 16 rows}
     CUtensorMap za, h;                         // fp16 activations [BI, K], box {64 halfs, 64 rows}
     CUtensorMap pin16;                         // fp16 [BI, Hd], box {64 halfs, 16 rows}
+    CUtensorMap pin64;                         // the same matrix, box {64 halfs, 64 rows} (MULTI phase D)
 };
 
 // LayerNorm + ELU of one row held as v[4] per consumer thread (features tid + 256 i); writes fp32 (fp16-representable) and
@@ -75,13 +83,17 @@ __device__ void ln_elu_row(float (&v)[4], int N, const float* __restrict__ gamma
     if (threadIdx.x == 0) { *mean_out = mean; *rstd_out = rstd; }
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_fwd_args a, const __grid_constant__ FwdMaps maps,
                                                                  const int KS) {
+    constexpr int TMEM_COLS = MULTI ? 512 : 128;
+    constexpr int HS = MULTI ? HB : BROWS;                  // row stride of hcs
+    constexpr int DR = MULTI ? 64 : 16;                     // batch rows of one phase-D pass
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* sh = (float*)(smem + OFF_SH);
     int* sidx = (int*)(smem + OFF_SIDX);
-    float* hcs = (float*)(smem + OFF_HC);                   // hcs[r * BROWS + b]
+    float* hcs = (float*)(smem + OFF_HC);                   // hcs[r * HS + b]
     float* part = (float*)(smem + OFF_PART);                // [2][Hd]
     float* lgs = (float*)(smem + OFF_LOG);                  // lgs[rb * 32 + class]
     float* gis = (float*)(smem + OFF_GI);                   // gis[(gate * 16 + r) * 65 + b]
@@ -118,8 +130,11 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
     const int RB = (BI + R - 1) / R;                                                                     // rows per such CTA
     const bool inD = c < G * R;
     const int g9 = c / R, sub9 = c % R, b9_0 = sub9 * RB, b9_1 = min(BI, b9_0 + RB);
+    const int NBB = MULTI ? (BI + BROWS - 1) / BROWS : 1;                                                // blocks of batch rows
+    const int NDC = !inD ? 0 : (MULTI ? max(0, (b9_1 - b9_0 + DR - 1) / DR) : 1);                        // phase-D passes
+    const int ASTEP = MULTI ? P : (1 << 30);                                                             // row owners' stride
 
-    for (int o = tid; o < nu * BI; o += NT) hcs[(o % nu) * BROWS + o / nu] = __ldcg(a.hin + (long)(o / nu) * D + u4_0 + o % nu);
+    for (int o = tid; o < nu * BI; o += NT) hcs[(o % nu) * HS + o / nu] = __ldcg(a.hin + (long)(o / nu) * D + u4_0 + o % nu);
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
@@ -139,7 +154,8 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         return j;
     };
     auto job_d = [&]() {
-        JobF j; j.ntile = inD ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = &maps.pin16; j.xmap[1] = &maps.pin16; j.xrow0 = b9_0; j.xrows = 16;
+        JobF j; j.ntile = inD ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = MULTI ? &maps.pin64 : &maps.pin16; j.xmap[1] = j.xmap[0];
+        j.xrow0 = b9_0; j.xrows = DR;
         j.xf16 = 1; j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wpm; j.row0[i] = g9 * C + 16 * i; }
         return j;
@@ -150,13 +166,14 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         if (lane == 0) {
             unsigned epoch = 0;
             // prologue: barrier 1 publishes h16 = fp16(h_0); then the phase-C job computes gh_0 partials; barrier 2
-            { const JobF j = job_c(); if (j.nkb) produce(ring, j, a.ws_barrier, 1); }
+            // (a further block of batch rows / pass of phase D is the same job with the activation box shifted)
+            { const JobF j = job_c(); if (j.nkb) for (int bb = 0; bb < NBB; ++bb) produce(ring, j, a.ws_barrier, 1, bb * BROWS); }
             epoch = 2;
             for (int t = 0; t < T; ++t) {
                 // barriers of a step: after A (1), after B (2), after C (3), after C' (4), after D (5, not on the last step)
-                { const JobF j = job_b(); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 1); }
-                { const JobF j = job_c(); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 2); }
-                { const JobF j = job_d(); if (j.nkb) produce(ring, j, a.ws_barrier, epoch + 4); }
+                { const JobF j = job_b(); if (j.nkb) for (int bb = 0; bb < NBB; ++bb) produce(ring, j, a.ws_barrier, epoch + 1, bb * BROWS); }
+                { const JobF j = job_c(); if (j.nkb) for (int bb = 0; bb < NBB; ++bb) produce(ring, j, a.ws_barrier, epoch + 2, bb * BROWS); }
+                { const JobF j = job_d(); if (j.nkb) for (int rc = 0; rc < NDC; ++rc) produce(ring, j, a.ws_barrier, epoch + 4, rc * DR); }
                 epoch += 5;
             }
         }
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
     auto phase_c = [&](bool want_gh, bool want_y2) {
         const JobF j = job_c();
         if (j.nkb == 0) return;
-        consume_umma<2, 64>(ring, j, tmem, accbar, accpar);
+        for (int bb = 0; bb < NBB; ++bb) consume_umma<2, 64>(ring, j, tmem + (uint32_t)(bb * 128), accbar, accpar, bb == NBB - 1);
         accpar ^= 1;
         // warp w reads UMMA tile (w >> 2), TMEM lane quarter (w & 3): thread = one weight row x 64 batch columns
         const int ut = warp >> 2, quarter = warp & 3;
@@ -186,15 +203,17 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
             const int f = f6_0 + (slot - 12) * 16 + rr;
             if (want_y2 && f < f6_1) { dst = a.ws_y2part + (long)ks * BI * Hd + f; bstride = Hd; }
         }
+        for (int bb = 0; bb < NBB; ++bb) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            uint32_t r[32];
-            tc_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ut * 64 + cc * 32), r);
-            if (dst) {
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t r[32];
+                tc_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(bb * 128 + ut * 64 + cc * 32), r);
+                if (dst) {
 #pragma unroll
-                for (int jb = 0; jb < 32; ++jb) {
-                    const int b = cc * 32 + jb;
-                    if (b < BI) dst[(long)b * bstride] = __uint_as_float(r[jb]);
+                    for (int jb = 0; jb < 32; ++jb) {
+                        const int b = bb * BROWS + cc * 32 + jb;
+                        if (b < BI) dst[(long)b * bstride] = __uint_as_float(r[jb]);
+                    }
                 }
             }
         }
@@ -210,10 +229,10 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
 
     for (int t = 0; t < T; ++t) {
         // ---- phase A (CTA b < BI): x1 = mask * gather(WzT, idx_{t-1}) + b_z + aa_t ; LayerNorm + ELU -> za
-        if (c < BI) {
-            const int b = c;
+        for (int b = c; b < BI; b += ASTEP) {
             const long row = (long)t * BI + b;
             float v[4];
+            if (MULTI && b != c) cons_sync();                             // sidx / part of my previous row are free again
             if (t > 0) {
                 const float m = a.mask[row];
                 for (int gg = tid; gg < G; gg += NCT) sidx[gg] = __ldcg(a.idx + ((long)(t - 1) * BI + b) * G + gg);
@@ -272,13 +291,15 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         {
             const JobF j = job_b();
             if (j.nkb > 0) {
-                consume_umma<1, 64>(ring, j, tmem, accbar, accpar);
+                for (int bb = 0; bb < NBB; ++bb) consume_umma<1, 64>(ring, j, tmem + (uint32_t)(bb * 64), accbar, accpar, bb == NBB - 1);
                 accpar ^= 1;
+              for (int bb = 0; bb < NBB; ++bb) {
+                if (MULTI && bb > 0) cons_sync();                          // gis of the previous block has been read
                 // rows 0..47 of the UMMA tile = (gate, unit): quarters 0 and 1; warps w and w + 4 take 32 batch columns each
                 if ((warp & 3) < 2) {
                     const int quarter = warp & 3, cc = warp >> 2, urow = quarter * 32 + lane;
                     uint32_t r[32];
-                    tc_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
+                    tc_ld_32x32b_x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(bb * 64 + cc * 32), r);
                     if (urow < 48) {
 #pragma unroll
                         for (int jb = 0; jb < 32; ++jb) gis[urow * 65 + cc * 32 + jb] = __uint_as_float(r[jb]);
@@ -287,32 +308,49 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
                 tc_fence_before();
                 cons_sync();
                 // gate math: one (unit, batch row) per thread iteration, unit fastest (coalesced global accesses)
-                for (int o = tid; o < nu * BI; o += NCT) {
-                    const int r = o % nu, b = o / nu, u = u4_0 + r;
-                    const long row = (long)t * BI + b;
-                    const float m = t > 0 ? a.mask[row] : 1.f;              // h_0 arrives already masked
-                    const float mn = t + 1 < T ? a.mask[row + BI] : 0.f;
-                    float gh0 = 0.f, gh1 = 0.f, gh2 = 0.f;
-                    for (int k = 0; k < KS; ++k) {                          // k-slice partials of phase C (threads run over u: coalesced)
-                        const float* gp = a.ws_ghpart + ((long)k * BI + b) * D3 + u;
-                        gh0 += __ldcg(gp); gh1 += __ldcg(gp + D); gh2 += __ldcg(gp + 2 * D);
+                const int nb = MULTI ? min(BROWS, BI - bb * BROWS) : BI;
+                // (the k-slice partials of up to four (unit, row) pairs are requested before any of them is used: the loop is
+                //  bound by the latency of those L2 reads, and the stores below would otherwise order them pair after pair)
+                for (int o0 = tid; o0 < nu * nb; o0 += 4 * NCT) {
+                    float gh[4][3];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int o = o0 + q * NCT;
+                        gh[q][0] = gh[q][1] = gh[q][2] = 0.f;
+                        if (o < nu * nb) {
+                            const int u = u4_0 + o % nu, b = bb * BROWS + o / nu;
+                            for (int k = 0; k < KS; ++k) {                  // threads run over u: coalesced
+                                const float* gp = a.ws_ghpart + ((long)k * BI + b) * D3 + u;
+                                gh[q][0] += __ldcg(gp); gh[q][1] += __ldcg(gp + D); gh[q][2] += __ldcg(gp + 2 * D);
+                            }
+                        }
                     }
-                    const float ghr = m * gh0 + a.b_hh[u];
-                    const float ghu = m * gh1 + a.b_hh[D + u];
-                    const float ghn = m * gh2 + a.b_hh[2 * D + u];
-                    const float rg_ = pd_sigmoid(gis[(0 * 16 + r) * 65 + b] + a.b_ih[u] + ghr);
-                    const float ug_ = pd_sigmoid(gis[(1 * 16 + r) * 65 + b] + a.b_ih[D + u] + ghu);
-                    const float ng_ = tanhf(gis[(2 * 16 + r) * 65 + b] + a.b_ih[2 * D + u] + rg_ * ghn);
-                    const float hp = hcs[r * BROWS + b];
-                    const __half hh = __float2half_rn((1.f - ug_) * ng_ + ug_ * hp);
-                    const float hn = __half2float(hh);
-                    a.feat[row * F + u] = hn;
-                    h16[(long)b * D + u] = hh;
-                    hcs[r * BROWS + b] = hn * mn;
-                    if (t + 1 < T) a.hin[(row + BI) * D + u] = hn * mn;
-                    float* gt = a.gates + row * 4 * D;
-                    gt[u] = rg_; gt[D + u] = ug_; gt[2 * D + u] = ng_; gt[3 * D + u] = ghn;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int o = o0 + q * NCT;
+                        if (o >= nu * nb) break;
+                        const int r = o % nu, bl = o / nu, b = bb * BROWS + bl, u = u4_0 + r;
+                        const long row = (long)t * BI + b;
+                        const float m = t > 0 ? a.mask[row] : 1.f;              // h_0 arrives already masked
+                        const float mn = t + 1 < T ? a.mask[row + BI] : 0.f;
+                        const float ghr = m * gh[q][0] + a.b_hh[u];
+                        const float ghu = m * gh[q][1] + a.b_hh[D + u];
+                        const float ghn = m * gh[q][2] + a.b_hh[2 * D + u];
+                        const float rg_ = pd_sigmoid(gis[(0 * 16 + r) * 65 + bl] + a.b_ih[u] + ghr);
+                        const float ug_ = pd_sigmoid(gis[(1 * 16 + r) * 65 + bl] + a.b_ih[D + u] + ghu);
+                        const float ng_ = tanhf(gis[(2 * 16 + r) * 65 + bl] + a.b_ih[2 * D + u] + rg_ * ghn);
+                        const float hp = hcs[r * HS + b];
+                        const __half hh = __float2half_rn((1.f - ug_) * ng_ + ug_ * hp);
+                        const float hn = __half2float(hh);
+                        a.feat[row * F + u] = hn;
+                        h16[(long)b * D + u] = hh;
+                        hcs[r * HS + b] = hn * mn;
+                        if (t + 1 < T) a.hin[(row + BI) * D + u] = hn * mn;
+                        float* gt = a.gates + row * 4 * D;
+                        gt[u] = rg_; gt[D + u] = ug_; gt[2 * D + u] = ng_; gt[3 * D + u] = ghn;
+                    }
                 }
+              }
             }
         }
         grid_barrier(a.ws_barrier, epoch);                                      // (2) h' complete
@@ -324,8 +362,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         clk.lap(3);
 
         // ---- phase C' (CTA b < BI): y2 = partial sums + b_ph + ea_t ; LayerNorm + ELU -> pin
-        if (c < BI) {
-            const int b = c;
+        for (int b = c; b < BI; b += ASTEP) {
             const long row = (long)t * BI + b;
             float v[4];
 #pragma unroll
@@ -345,25 +382,28 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         clk.lap(4);
 
         // ---- phase D (latent-group owners): logits of group g for my rows, softmax, argmax(p / q) -> post, idx, z
-        if (inD) {
+        for (int rc = 0; rc < NDC; ++rc) {
             const JobF j = job_d();
             float acc[1][2][4];
-            const bool act = warp < 2 && warp * 16 < C;                         // warp = 16 classes of the group, both n8-tiles of my rows
-            consume_f16<1, 2>(ring, j, warp, 0, act, acc);
+            if (MULTI && rc > 0) cons_sync();                                   // lgs of the previous pass has been read
+            // warp = 16 classes of the group x two n8-tiles of batch rows: 16 rows per pass need warps 0 and 1, 64 rows all eight
+            const int ctile = MULTI ? (warp & 1) : warp, n8_0 = MULTI ? (warp >> 1) * 2 : 0;
+            const bool act = (MULTI || warp < 2) && ctile * 16 < C;
+            consume_f16<1, 2>(ring, j, ctile, n8_0, act, acc);
             if (act) {
                 const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
                 for (int jn = 0; jn < 2; ++jn)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int cls = 16 * warp + g + 8 * (e >> 1), rb = jn * 8 + 2 * tq + (e & 1);
+                        const int cls = 16 * ctile + g + 8 * (e >> 1), rb = (n8_0 + jn) * 8 + 2 * tq + (e & 1);
                         if (cls < C) lgs[rb * 32 + cls] = acc[0][jn][e];
                     }
             }
             cons_sync();
             const float pbias = lane < C ? a.b_pm[g9 * C + lane] : 0.f;
-            for (int rb = warp; rb < b9_1 - b9_0; rb += NCW) {
-                const int b = b9_0 + rb;
+            for (int rb = warp; rb < min(DR, b9_1 - b9_0 - rc * DR); rb += NCW) {
+                const int b = b9_0 + rc * DR + rb;
                 const long row = (long)t * BI + b;
                 const bool valid = lane < C;
                 const float q = valid ? a.noise[row * Z + g9 * C + lane] : 1.f;
@@ -408,11 +448,13 @@ extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void*
     PdDeviceGuard guard(h);
     constexpr size_t SMEM_REQ = (size_t)SMEM_BYTES + 1024;
     if (!h->k1_configured) {
-        if (cudaFuncSetAttribute(rssm_unroll_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_REQ) != cudaSuccess)
+        if (cudaFuncSetAttribute(rssm_unroll_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_REQ) != cudaSuccess ||
+            cudaFuncSetAttribute(rssm_unroll_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_REQ) != cudaSuccess)
             PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: cannot reserve %d bytes of shared memory", (int)SMEM_REQ);
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rssm_unroll_fwd3_kernel, NT, SMEM_REQ);
-        h->k1_ctas = per_sm > 0 ? h->num_sms : 0;             // one CTA per SM
+        int per_sm = 0, per_sm_m = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rssm_unroll_fwd3_kernel<false>, NT, SMEM_REQ);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_m, rssm_unroll_fwd3_kernel<true>, NT, SMEM_REQ);
+        h->k1_ctas = (per_sm > 0 && per_sm_m > 0) ? h->num_sms : 0;             // one CTA per SM
         h->k1_configured = 1;
     }
     const int P = h->k1_ctas;
@@ -421,9 +463,11 @@ extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void*
     const int KS = (a->D % (KSPLIT * KB) == 0 && P >= KSPLIT) ? KSPLIT : 1;
     const int RG = P / KS;
     const int R = P / a->G < 4 ? (P / a->G < 1 ? 1 : P / a->G) : 4;
-    const bool ok = a->T >= 1 && a->BI >= 1 && a->BI <= BROWS && a->BI <= P && a->I >= 1 && a->BI % a->I == 0 &&
+    // one block of batch rows: the single-block kernel; up to four (IWAE): the MULTI instantiation
+    const bool multi = !(a->BI <= BROWS && a->BI <= P && (a->BI + R - 1) / R <= 16);
+    const bool ok = a->T >= 1 && a->BI >= 1 && a->BI <= HB && a->I >= 1 && a->BI % a->I == 0 &&
                     a->Hd <= 4 * NCT && a->Hd % 8 == 0 && a->D % 8 == 0 && a->C >= 1 && a->C <= 32 && a->G >= 1 && a->G <= P &&
-                    (a->BI + R - 1) / R <= 16 && (a->D + P - 1) / P <= 16 && (a->D + RG - 1) / RG <= 64 &&
+                    (a->D + P - 1) / P <= 16 && (a->D + RG - 1) / RG <= 64 &&
                     (a->Hd + RG - 1) / RG <= 32 && Z >= 1 && a->ws_ghpart && a->ws_y2part && a->ws_wzT16;
     if (!ok)
         PD_FAIL(h, PD_ERR_UNSUPPORTED, "pd_rssm_unroll_fwd: shape T=%d BI=%d D=%d Hd=%d G=%d C=%d outside the kernel's limits",
@@ -438,13 +482,15 @@ extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void*
     if (!rc) rc = make_map(h, who, &maps.za, a->ws_za16, a->BI, a->Hd, BROWS, true);
     if (!rc) rc = make_map(h, who, &maps.h, a->ws_h16, a->BI, a->D, BROWS, true);
     if (!rc) rc = make_map(h, who, &maps.pin16, a->ws_pin16, a->BI, a->Hd, 16, true);
+    if (!rc) rc = make_map(h, who, &maps.pin64, a->ws_pin16, a->BI, a->Hd, BROWS, true);
     if (rc) return rc;
     if (cudaMemsetAsync(a->ws_barrier, 0, 16 * sizeof(unsigned), s) != cudaSuccess)
         PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: memset failed");
     pd_rssm_fwd_args args = *a;
     int ksv = KS;
     void* kargs[] = {(void*)&args, (void*)&maps, (void*)&ksv};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)rssm_unroll_fwd3_kernel, dim3(P), dim3(NT), kargs, SMEM_REQ, s);
+    const void* fn = multi ? (const void*)rssm_unroll_fwd3_kernel<true> : (const void*)rssm_unroll_fwd3_kernel<false>;
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(P), dim3(NT), kargs, SMEM_REQ, s);
     if (e != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: %s", cudaGetErrorString(e));
     PD_CHECK_LAUNCH(h, "pd_rssm_unroll_fwd");
     return PD_OK;

@@ -784,7 +784,7 @@ class Dreamer(nn.Module):
     _scratch_ns = ""          # name space of the shared MLP scratch buffers (one per concurrent branch)
 
     # The posterior unroll runs as ONE cooperative kernel (csrc/pd_rssm_fwd3.cu) when the shape fits its limits
-    # (B*I <= 64 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
+    # (B*I <= 256 rows, ...); PD_B200_PERSISTENT_RSSM=0 selects the chain of 9 launches per timestep instead.
     persistent_rssm = os.environ.get("PD_B200_PERSISTENT_RSSM", "1") != "0"
 
     # BPTT through the posterior unroll as ONE cooperative kernel (csrc/pd_rssm_bptt.cu): opt-in with PD_B200_PERSISTENT_BPTT=1.
@@ -818,8 +818,9 @@ class Dreamer(nn.Module):
         ks = 4 if d.D % 256 == 0 and P >= 4 else 1
         R = max(1, min(4, P // d.G))
         cd = lambda a_, b_: -(-a_ // b_)
-        return (BI <= min(64, P) and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and d.G <= P and
-                cd(BI, R) <= 16 and cd(d.D, P) <= 16 and cd(d.D, P // ks) <= 64 and cd(d.Hd, P // ks) <= 32 and
+        # batch rows (B x iwae_samples) beyond one 64-row MMA operand are taken in blocks by the kernel, up to 256
+        return (BI <= 256 and d.Hd <= 1024 and d.Hd % 8 == 0 and d.D % 8 == 0 and d.C <= 32 and d.G <= P and
+                cd(d.D, P) <= 16 and cd(d.D, P // ks) <= 64 and cd(d.Hd, P // ks) <= 32 and
                 getattr(self, "_k1_wzT", None) is not None)
 
     def _ov(self, bit):

@@ -183,16 +183,18 @@ def test_full_atari_shape_subbatch_parity_with_oracle(persistent):
         assert v < 2e-3, (k, v)
 
 
-def test_persistent_rssm_kernel_matches_the_per_step_chain_at_full_size():
-    """pd_rssm_unroll_fwd (one cooperative kernel, fp16 mma.sync) against the chain of per-timestep launches (TF32 tcgen05)
-    on the Atari shape, same weights / batch / noise: both round operands to 10 mantissa bits, so logits agree to
-    accumulation order and the sampled indices are the same except at numerical near-ties."""
+@pytest.mark.parametrize("preset", ("atari", "atari_iwae"), ids=("atari", "atari_iwae4_BI200"))
+def test_persistent_rssm_kernel_matches_the_per_step_chain_at_full_size(preset):
+    """pd_rssm_unroll_fwd (one cooperative kernel, fp16 tcgen05 / mma.sync) against the chain of per-timestep launches (TF32
+    tcgen05) on the Atari shape, same weights / batch / noise: both round operands to 10 mantissa bits, so logits agree to
+    accumulation order and the sampled indices are the same except at numerical near-ties.  `atari_iwae` (B=50 x 4 samples
+    = 200 batch rows) exercises the kernel's batch-row blocks (4 blocks of 64) and strided row owners (200 rows > 148 CTAs)."""
     from pydreamer_b200.config import make_conf
     from pydreamer_b200.replay import synthetic_batch
     from oracle.weights import seeded_state_dict
 
-    conf = make_conf("atari", device=DEV)
-    T, B, H = conf.batch_length, conf.batch_size, conf.imag_horizon
+    conf = make_conf(preset, device=DEV)
+    T, B, H, I = conf.batch_length, conf.batch_size * conf.iwae_samples, conf.imag_horizon, conf.iwae_samples
     D, G, C, A = conf.deter_dim, conf.stoch_dim, conf.stoch_discrete, conf.action_dim
     Z, N, Hd = G * C, T * B, conf.hidden_dim
     obs = synthetic_batch(conf, seed=3, device=DEV)

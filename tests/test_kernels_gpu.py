@@ -51,6 +51,8 @@ def ref():
 
 GEMM_SHAPES = [(128, 128, 32), (128, 128, 256), (50, 1000, 1024), (300, 6144, 1000), (130, 264, 100), (64, 48, 48),
                (257, 1000, 2048), (2500, 400, 3072), (900, 108, 48),
+               # MN-major operands as 3-D TMA boxes: tiles with full 32-column groups followed by groups past the end
+               (160, 96, 200),
                # large enough for the 2-CTA (cta_group::2) 256x256 kernel when PD_GEMM_2CTA=1
                (1024, 512, 256), (2500, 6144, 96), (640, 1000, 1000)]
 

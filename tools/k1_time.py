@@ -11,7 +11,7 @@ obs = synthetic_batch(conf, seed=1, device="cuda:0")
 model = Dreamer(conf).to("cuda:0")
 model.persistent_rssm = True
 model.overlap = 0
-state = model.init_state(conf.batch_size)
+state = model.init_state(conf.batch_size * conf.iwae_samples)
 with torch.no_grad():
     model.training_step(obs, state)
 ops = model.ops
