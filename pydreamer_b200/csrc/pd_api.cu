@@ -33,6 +33,8 @@ int pd_create(int device_ordinal, pd_handle** out) {
     if (const char* e2 = getenv("PD_GEMM_2CTA")) h->gemm_2cta = atoi(e2);
     h->gemm_mn3 = 1;
     h->gemm_conv_k64 = 1;
+    h->gemm_2cta_min_m = 384;
+    if (const char* e6 = getenv("PD_GEMM_2CTA_MINM")) h->gemm_2cta_min_m = atoi(e6);
     if (const char* e4 = getenv("PD_GEMM_CONV_K64")) h->gemm_conv_k64 = atoi(e4);
     if (const char* e3 = getenv("PD_GEMM_MN3")) h->gemm_mn3 = atoi(e3);
     cudaSetDevice(device_ordinal);

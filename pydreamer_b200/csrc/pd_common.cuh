@@ -23,6 +23,7 @@ struct pd_handle {
     void* encode_im2col;      // cuTensorMapEncodeIm2col entry point (lazy)
     int gemm_smem_configured;
     int gemm_2cta;            // allow the cta_group::2 256x256 kernel for large problems
+    int gemm_2cta_min_m;      // smallest M that goes to the 2-CTA kernel (PD_GEMM_2CTA_MINM, default 384: three of four 128-row tiles real)
     int gemm_conv_k64;        // pd_conv_gemm modes 2 / 3 with 64-pixel k-blocks (PD_GEMM_CONV_K64=0: 32)
     int gemm_mn3;             // MN-major operands as one 3-D TMA box per tile (PD_GEMM_MN3=0: four 2-D boxes, the round-1 form)
     int gemm2_smem_configured;

@@ -935,6 +935,7 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
         if (!o_mn) rc = make_map(h, &tmB, O, (uint64_t)Ktot, (uint64_t)N, (uint64_t)ldo, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
         else       rc = make_map(h, &tmB, O, (uint64_t)N, (uint64_t)Ktot, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
+        if (o_mn && h->gemm_mn3) { rc = make_map3(h, &tmB3, O, (uint64_t)N, (uint64_t)Ktot, (uint64_t)ldo, &g.b3_on, &g.b3_part); if (rc) return rc; }
     } else if (mode == 2) {
         M = k * k * g.cv_cpad; N = ODIM;
         g.a_mode = 2; g.a_mn = 1; g.b_mode = 0; g.b_mn = 1;
@@ -1046,7 +1047,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     }
     if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, 8);   // split-K over idle SMs / partial waves
     // Large tiles-rich problems go to the 2-CTA (cta_group::2) 256x256 kernel; it needs a TMA-addressable C.
-    int use2 = h->gemm_2cta && g.tma_store && M >= 512 && N >= 256 && !g.extras_on_split0;
+    int use2 = h->gemm_2cta && g.tma_store && M >= h->gemm_2cta_min_m && N >= 256 && !g.extras_on_split0;
     if (use2) {
         int tiles2 = pd_cdiv(M, 256) * pd_cdiv(N, BN2);
         int pairs_avail = h->num_sms / 2;

@@ -53,6 +53,8 @@ GEMM_SHAPES = [(128, 128, 32), (128, 128, 256), (50, 1000, 1024), (300, 6144, 10
                (257, 1000, 2048), (2500, 400, 3072), (900, 108, 48),
                # MN-major operands as 3-D TMA boxes: tiles with full 32-column groups followed by groups past the end
                (160, 96, 200),
+               # M in [384, 512): 2-CTA kernel with a quarter of the second 256-row tile past the end
+               (400, 512, 96), (450, 300, 64),
                # large enough for the 2-CTA (cta_group::2) 256x256 kernel when PD_GEMM_2CTA=1
                (1024, 512, 256), (2500, 6144, 96), (640, 1000, 1000)]
 

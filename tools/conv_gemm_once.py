@@ -33,7 +33,9 @@ def timed(fn):
     return round(e0.elapsed_time(e1) * 1000, 1)
 
 
+WkT = Wk.t().contiguous()
 runs = dict(conv_mode1=lambda: ops.conv_gemm(1, X, k, Wk, C1),
+            conv_mode1_w_mn=lambda: ops.conv_gemm(1, X, k, WkT, C1, o_mn=True),
             conv_mode2=lambda: ops.conv_gemm(2, X, k, Ot, C2),
             conv_mode3=lambda: ops.conv_gemm(3, X, k, Ot, C3),
             gemm_f16_2cta=lambda: ops.gemm_f16(A16, B16, Cf))
@@ -43,6 +45,6 @@ torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 us = {n: timed(f) for n, f in runs.items()}
 torch.cuda.cudart().cudaProfilerStop()
-flops = dict(conv_mode1=2.0 * pixels * K * odim, conv_mode2=2.0 * pixels * K * odim, conv_mode3=2.0 * pixels * K * odim,
+flops = dict(conv_mode1=2.0 * pixels * K * odim, conv_mode1_w_mn=2.0 * pixels * K * odim, conv_mode2=2.0 * pixels * K * odim, conv_mode3=2.0 * pixels * K * odim,
              gemm_f16_2cta=2.0 * 2500 * 6144 * 2048)
 print(json.dumps({n: dict(us=us[n], tflops=round(flops[n] / us[n] / 1e6, 1)) for n in runs}))
