@@ -239,6 +239,20 @@ int pd_col2im_imgloss_t(pd_handle* h, int NB, int Hin, int Win, int Cc, int k, c
 /* dy <- dy * act'(y) in place (act from output y), db[c] += column sums of the result. */
 int pd_bias_act_bwd(pd_handle* h, long M, int N, float* dy, long lddy, const float* y, long ldy,
                     int act, float* db, void* stream);
+/* The ELU backward + bias gradient of the layer BELOW fused into the kernel that produces that layer's output gradient
+ * (instead of a separate pd_bias_act_bwd pass over the gradient image; PD_B200_FUSE_ACTBWD=0 composes the two launches):
+ *   pd_gemm_actbwd:      C = (A B^T) .* elu'(dact), dbias[n] += sum_m C[m, n]      (Linear / explicit-column deconv dX;
+ *                        decoders.py:128-155 backward, autograd of nn.ELU + bias)
+ *   pd_conv_gemm_actbwd: the same for pd_conv_gemm mode 1 (ConvTranspose2d input gradient gathered by TMA im2col)
+ *   pd_col2im_actbwd:    out = fold(col) .* elu'(dact), dbias[c] += sum over pixels  (Conv2d input gradient; encoders.py:80-90
+ *                        backward); out / dact contiguous NHWC [NB, Hout, Wout, Cc], Hout >= 2(Hin-1)+k (rows a stride-2 conv never read get 0)
+ * dact is the saved forward output of the layer below (ELU derivative from the output: y > 0 ? 1 : y + 1). */
+int pd_gemm_actbwd(pd_handle* h, int M, int N, int K, const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn,
+                   float* C, long ldc, const float* dact, long lddact, float* dbias, void* stream);
+int pd_conv_gemm_actbwd(pd_handle* h, int NB, int H, int W, int C, int k, const float* X, const float* O, long ldo, int o_mn,
+                        int odim, float* Cmat, long ldc, const float* dact, long lddact, float* dbias, void* stream);
+int pd_col2im_actbwd(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* col, long ldcol,
+                     const float* dact, float* dbias, float* out, void* stream);
 /* generic 4-D permutation copy out[perm(i)] (+)= in[i];  dims (HOST int[4]) of `in`, perm[j] (HOST) = source axis of out axis j. */
 int pd_permute4(pd_handle* h, const float* in, float* out, const int* dims, const int* perm,
                 const long* in_strides /* HOST long[4] element strides of `in`, or NULL = contiguous */,

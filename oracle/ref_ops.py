@@ -339,6 +339,21 @@ class RefOps:
         if db is not None:
             db.add_(dy.sum(0))
 
+    def gemm_actbwd(self, A, B, C, dact, dbias, *, a_mn=False, b_mn=False):
+        self.gemm(A, B, C, a_mn=a_mn, b_mn=b_mn)
+        self.bias_act_bwd(C, dact, ACT_ELU, dbias)
+        return C
+
+    def conv_gemm_actbwd(self, X, k, O, Cmat, dact, dbias, *, o_mn=False):
+        self.conv_gemm(1, X, k, O, Cmat, o_mn=o_mn)
+        self.bias_act_bwd(Cmat, dact, ACT_ELU, dbias)
+        return Cmat
+
+    def col2im_actbwd(self, col, Hin, Win, k, dact, dbias, out):
+        self.col2im(col, Hin, Win, k, None, ACT_NONE, out, round_out=False)
+        NB, Hout, Wout, Cc = out.shape
+        self.bias_act_bwd(out.view(-1, Cc), dact.reshape(-1, Cc), ACT_ELU, dbias)
+
     def permute4(self, inp, out, perm, accumulate=False, round_out=False):
         v = inp.permute(*perm)
         if accumulate:

@@ -24,6 +24,7 @@ struct pd_handle {
     int gemm_smem_configured;
     int gemm_2cta;            // allow the cta_group::2 256x256 kernel for large problems
     int gemm_2cta_min_m;      // smallest M that goes to the 2-CTA kernel (PD_GEMM_2CTA_MINM, default 384: three of four 128-row tiles real)
+    int fuse_actbwd;          // ELU backward + bias gradient inside the producing GEMM / col2im (PD_B200_FUSE_ACTBWD=0: separate pass)
     int gemm_conv_k64;        // pd_conv_gemm modes 2 / 3 with 64-pixel k-blocks (PD_GEMM_CONV_K64=0: 32)
     int gemm_mn3;             // MN-major operands as one 3-D TMA box per tile (PD_GEMM_MN3=0: four 2-D boxes, the round-1 form)
     int gemm2_smem_configured;
@@ -148,6 +149,12 @@ struct PdEpilogue {
     int accumulate;      // 0: C = v ; 1: atomicAdd(C, v) (split-K safe, no bias/act)
     int c_zeroed;        // caller cleared C already (lets a skinny-M split-K launch skip its memset)
     int c_f16;           // C is an fp16 matrix (ldc in halfs): the epilogue converts and stores rows with vector stores
+    // backward through the ELU that FOLLOWED the layer whose input gradient this GEMM produces (pd_gemm_actbwd):
+    // v *= elu'(dact[m, n]) (dact = that layer's saved output), then dbias[n] += sum_m v — what pd_bias_act_bwd does in a
+    // separate pass over C
+    const float* dact;
+    long lddact;
+    float* dbias;
 };
 
 __device__ __forceinline__ float pd_epi_value(const PdEpilogue& e, int row, int col, float acc) {

@@ -150,6 +150,60 @@ __global__ void col2im_v4_kernel(long total4, int Hin, int Win, int Hout, int Wo
     }
 }
 
+// Conv2d input gradient folded back from its column form AND taken through the ELU of the layer below in one pass
+// (encoders.py:80-90 backward): out = fold(col) * elu'(dact), dbias[c] += sum over pixels — what pd_col2im followed by
+// pd_bias_act_bwd do in two passes over the gradient image.  out / dact: contiguous NHWC.  192 threads per block and
+// 192 % (Cc / 4) == 0: a thread keeps its channel quad over the grid-stride loop, so the bias sums stay in registers.
+__global__ void __launch_bounds__(192) col2im_actbwd_kernel(long total4, int Hin, int Win, int Hout, int Wout, int C4, int k,
+                                                           const float* __restrict__ col, long ldcol,
+                                                           const float* __restrict__ dact, int round_out,
+                                                           float* __restrict__ out, float* dbias) {
+    const int Cc = C4 * 4;
+    const int c4 = threadIdx.x % C4;
+    float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        long t = idx / C4;
+        const long pix = t;
+        int x = (int)(t % Wout);
+        t /= Wout;
+        int y = (int)(t % Hout);
+        long n = t / Hout;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 tap[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int kh = (y & 1) + 2 * a;
+            const int iy = (y - kh) >> 1;
+            const bool oky = kh < k && iy >= 0 && iy < Hin;
+#pragma unroll
+            for (int bq = 0; bq < 3; ++bq) {
+                const int kw = (x & 1) + 2 * bq;
+                const int ix = (x - kw) >> 1;
+                tap[a * 3 + bq] = (oky && kw < k && ix >= 0 && ix < Win)
+                    ? ld_col4(col + ((n * Hin + iy) * Win + ix) * ldcol + (long)(kh * k + kw) * Cc + c4 * 4)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const float4 yv = *reinterpret_cast<const float4*>(dact + pix * Cc + c4 * 4);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { acc.x += tap[i].x; acc.y += tap[i].y; acc.z += tap[i].z; acc.w += tap[i].w; }
+        acc.x *= pd_elu_grad_from_out(yv.x); acc.y *= pd_elu_grad_from_out(yv.y);
+        acc.z *= pd_elu_grad_from_out(yv.z); acc.w *= pd_elu_grad_from_out(yv.w);
+        bs.x += acc.x; bs.y += acc.y; bs.z += acc.z; bs.w += acc.w;
+        if (round_out) { acc.x = pd_tf32(acc.x); acc.y = pd_tf32(acc.y); acc.z = pd_tf32(acc.z); acc.w = pd_tf32(acc.w); }
+        *reinterpret_cast<float4*>(out + pix * Cc + c4 * 4) = acc;
+    }
+    __shared__ float4 sh[192];
+    sh[threadIdx.x] = bs;
+    __syncthreads();
+    if (threadIdx.x < C4 && dbias) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = threadIdx.x; m < 192; m += C4) { s4.x += sh[m].x; s4.y += sh[m].y; s4.z += sh[m].z; s4.w += sh[m].w; }
+        atomicAdd(dbias + c4 * 4, s4.x); atomicAdd(dbias + c4 * 4 + 1, s4.y);
+        atomicAdd(dbias + c4 * 4 + 2, s4.z); atomicAdd(dbias + c4 * 4 + 3, s4.w);
+    }
+}
+
 __device__ __forceinline__ float col2im_gather(const float* __restrict__ col, long ldcol, long n, int y, int x, int c,
                                                int Hin, int Win, int Cc, int k) {
     float acc = 0.f;
@@ -361,6 +415,26 @@ int pd_col2im_t(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int 
     col2im_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         total, Hin, Win, Hout, Wout, Cc, k, col, ldcol, bias, act, round_out && h->round_ops, out, sN, sY, sX, sC);
     PD_CHECK_LAUNCH(h, "col2im");
+    return PD_OK;
+}
+
+int pd_col2im_actbwd(pd_handle* h, int NB, int Hin, int Win, int Hout, int Wout, int Cc, int k, const float* col, long ldcol,
+                     const float* dact, float* dbias, float* out, void* stream) {
+    if (!h) return PD_ERR_ARG;
+    PD_REQUIRE(h, col && dact && out && Cc >= 1 && k >= 1 && k <= 6, "pd_col2im_actbwd: bad arguments");
+    PD_REQUIRE(h, Hout >= (Hin - 1) * 2 + k && Wout >= (Win - 1) * 2 + k, "pd_col2im_actbwd: output smaller than the fold");
+    const long total = (long)NB * Hout * Wout * Cc;
+    const bool fused = h->fuse_actbwd && (Cc % 4) == 0 && (192 % (Cc / 4)) == 0 && (ldcol % 4) == 0 &&
+                       ((((uintptr_t)out) | ((uintptr_t)col) | ((uintptr_t)dact)) & 15) == 0;
+    if (!fused) {
+        int rc = pd_col2im(h, NB, Hin, Win, Hout, Wout, Cc, k, col, ldcol, nullptr, PD_ACT_NONE, 0, out, (long)Hout * Wout * Cc,
+                           (long)Wout * Cc, Cc, 1, stream);
+        if (rc) return rc;
+        return pd_bias_act_bwd(h, (long)NB * Hout * Wout, Cc, out, Cc, dact, Cc, PD_ACT_ELU, dbias, stream);
+    }
+    col2im_actbwd_kernel<<<grid_for(total / 4, 192, h->num_sms), 192, 0, (cudaStream_t)stream>>>(
+        total / 4, Hin, Win, Hout, Wout, Cc / 4, k, col, ldcol, dact, h->round_ops, out, dbias);
+    PD_CHECK_LAUNCH(h, "col2im_actbwd");
     return PD_OK;
 }
 

@@ -440,6 +440,20 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = pd_elu(v[j]);
                     }
+                    if (e.dact && row < g.M) {            // ELU backward of the layer below: v *= elu'(saved output)
+                        const float* yp = e.dact + (long)row * e.lddact + col0;
+                        if (((e.lddact & 3) == 0) && ((((uintptr_t)e.dact) & 15) == 0) && col0 + 32 <= g.N) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(yp) + j);
+                                v[4 * j] *= pd_elu_grad_from_out(q.x); v[4 * j + 1] *= pd_elu_grad_from_out(q.y);
+                                v[4 * j + 2] *= pd_elu_grad_from_out(q.z); v[4 * j + 3] *= pd_elu_grad_from_out(q.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (col0 + j < g.N) v[j] *= pd_elu_grad_from_out(__ldg(yp + j));
+                        }
+                    }
                     if (e.round_out) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
@@ -468,6 +482,15 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                          ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (e.dbias) {                        // bias gradient of the layer below: column sums of the staged box
+                        // (rows past M hold zeros; lane = column: 16-byte chunk (lane >> 2) of row r sits at chunk
+                        //  (lane >> 2) ^ (r & 7) of the swizzled box: conflict-free)
+                        float sacc = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r)
+                            sacc += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                        if (col0 + lane < g.N) atomicAdd(e.dbias + col0 + lane, sacc);
                     }
                     if (!BIG) sbuf ^= 1;
                 } else {
@@ -1027,7 +1050,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     // Skinny-M layers (the per-timestep RSSM GEMMs, M = B*I = 50) have too few output tiles to pull their
     // weights through more than a handful of SMs: split K over the idle SMs.  C is zeroed, every split adds its
     // partial product with red.global.add, split 0 also adds bias + residual.
-    if (!epi.accumulate && !epi.c_f16 && g.num_m == 1 && epi.act == PD_ACT_NONE && !epi.round_out && tiles * 2 <= h->num_sms &&
+    if (!epi.accumulate && !epi.c_f16 && !epi.dact && g.num_m == 1 && epi.act == PD_ACT_NONE && !epi.round_out && tiles * 2 <= h->num_sms &&
         g.kb_total >= 8) {
         int want = h->num_sms / tiles;
         if (const char* ms = getenv("PD_GEMM_SKINNY_MAXSPLIT")) { int v = atoi(ms); if (want > v) want = v; }   // tuning aid
@@ -1047,7 +1070,8 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     }
     if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, 8);   // split-K over idle SMs / partial waves
     // Large tiles-rich problems go to the 2-CTA (cta_group::2) 256x256 kernel; it needs a TMA-addressable C.
-    int use2 = h->gemm_2cta && g.tma_store && M >= h->gemm_2cta_min_m && N >= 256 && !g.extras_on_split0;
+    PD_REQUIRE(h, !epi.dact || (g.tma_store && !epi.c_f16 && !epi.accumulate), "pd_gemm(actbwd): needs a TMA-addressable fp32 C");
+    int use2 = h->gemm_2cta && g.tma_store && M >= h->gemm_2cta_min_m && N >= 256 && !g.extras_on_split0 && !epi.dact;
     if (use2) {
         int tiles2 = pd_cdiv(M, 256) * pd_cdiv(N, BN2);
         int pairs_avail = h->num_sms / 2;

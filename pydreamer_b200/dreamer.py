@@ -1164,10 +1164,12 @@ class Dreamer(nn.Module):
             hi, ho, k, ci, co = dgeo[li]
             xin = b("dec.x0", N, 32 * cd) if li == 0 else b(f"dec.d{li - 1}", N, hi, hi, ci).view(N * hi * hi, ci)
             dxin = b(f"bwd.dd{li}", N * hi * hi, ci)
+            # (li > 0: the ELU backward and the bias gradient of the deconv below ride in the input-gradient GEMM's epilogue)
+            below_bias = G(dec[2 * li].bias) if li > 0 else None
             if impl[li]:
                 with side():
                     ops.conv_gemm(2, dout4, k, xin, gdec[li])                          # weight gradient, rows (tap, co padded)
-                ops.conv_gemm(1, dout4, k, self._decw[li], dxin, o_mn=True)            # input gradient
+                ops.conv_gemm_actbwd(dout4, k, self._decw[li], dxin, xin, below_bias, o_mn=True)   # input gradient
             else:
                 if li == 0:
                     dcols = dout4.reshape(N, k * k * co)       # 5x5 input of a 5x5 kernel: im2col is the identity
@@ -1176,9 +1178,11 @@ class Dreamer(nn.Module):
                     ops.im2col(dout4, k, 0, dcols, round_out=True)
                 with side():
                     ops.gemm(dcols, xin, gdec[li], a_mn=True, b_mn=True, accumulate=True)
-                ops.gemm(dcols, self._decw[li], dxin, b_mn=True, round_out=(li == 0))
+                if li > 0:
+                    ops.gemm_actbwd(dcols, self._decw[li], dxin, xin, below_bias, b_mn=True)
+                else:
+                    ops.gemm(dcols, self._decw[li], dxin, b_mn=True, round_out=True)
             if li > 0:
-                ops.bias_act_bwd(dxin, xin, ACT_ELU, G(dec[2 * li].bias))       # bias of the previous deconv
                 dout4 = dxin.view(N, hi, hi, ci)
             else:
                 dx0 = dxin
@@ -1257,8 +1261,9 @@ class Dreamer(nn.Module):
             for li in (3, 2, 1, 0):
                 hin_, hout, ci, co = geo[li]
                 hw = hout * hout
-                act = b(f"enc.a{li}", NB * hw, co)[r0 * hw:r1 * hw]
-                ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
+                if li == 3:                 # (layers 2..0: done by the col2im that produced their output gradient)
+                    act = b(f"enc.a{li}", NB * hw, co)[r0 * hw:r1 * hw]
+                    ops.bias_act_bwd(da, act, ACT_ELU, G(enc[2 * li].bias))
                 if li == 0:
                     col = b(f"enc.col{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
                     ops.gemm(da, col, G(enc[0].weight).view(co, 16 * ci), a_mn=True, b_mn=True, accumulate=True)
@@ -1272,7 +1277,9 @@ class Dreamer(nn.Module):
                 dcol = b(f"bwd.dcol{li}", NB * hw, 16 * ci)[r0 * hw:r1 * hw]
                 ops.gemm(da, self._encw[li], dcol, b_mn=True)
                 da_prev = b(f"bwd.da{li - 1}", NB * hin_ * hin_, ci)[r0 * hin_ * hin_:r1 * hin_ * hin_]
-                ops.col2im(dcol, hout, hout, 4, None, ACT_NONE, da_prev.view(n, hin_, hin_, ci), round_out=False)
+                act_prev = b(f"enc.a{li - 1}", NB * hin_ * hin_, ci)[r0 * hin_ * hin_:r1 * hin_ * hin_]
+                # fold the column-form gradient back AND go through the ELU / bias of the layer below in the same pass
+                ops.col2im_actbwd(dcol, hout, hout, 4, act_prev, G(enc[2 * (li - 1)].bias), da_prev.view(n, hin_, hin_, ci))
                 da = da_prev
 
         def enc_bwd_end():

@@ -272,6 +272,45 @@ class NativeOps:
         self._ck(self.lib.pd_bias_act_bwd(self.h, M, N, _ptr(dy), _ld(dy), _ptr(y), _ld(y) if y is not None else 0,
                                           int(act), _ptr(db), self._s()), "pd_bias_act_bwd")
 
+    def gemm_actbwd(self, A, B, C, dact, dbias, *, a_mn=False, b_mn=False):
+        """C = (A B^T) * elu'(dact); dbias += column sums (pd_gemm_actbwd: GEMM + bias_act_bwd in one launch)."""
+        M, N = C.shape
+        K = A.shape[0] if a_mn else A.shape[1]
+        prof = self.gemm_profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._ck(self.lib.pd_gemm_actbwd(self.h, M, N, K, _ptr(A), _ld(A), int(a_mn), _ptr(B), _ld(B), int(b_mn), _ptr(C), _ld(C),
+                                         _ptr(dact), _ld(dact), _ptr(dbias), self._s()), "pd_gemm_actbwd")
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), 0)))
+        return C
+
+    def conv_gemm_actbwd(self, X, k, O, Cmat, dact, dbias, *, o_mn=False):
+        """pd_conv_gemm mode 1 followed by the ELU backward of the layer below and its bias gradient, one launch."""
+        NB, H, W, C = X.shape
+        assert X.is_contiguous()
+        odim = Cmat.shape[1]
+        prof = self.gemm_profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._ck(self.lib.pd_conv_gemm_actbwd(self.h, NB, H, W, C, int(k), _ptr(X), _ptr(O), _ld(O), int(o_mn), odim, _ptr(Cmat),
+                                              _ld(Cmat), _ptr(dact), _ld(dact), _ptr(dbias), self._s()), "pd_conv_gemm_actbwd")
+        if prof is not None:
+            e1.record()
+            P, Q = (H - k) // 2 + 1, (W - k) // 2 + 1
+            prof.append((e0, e1, 2.0 * NB * P * Q * k * k * C * odim, (NB * P * Q, odim, k * k * C, "conv1", int(o_mn), 0)))
+        return Cmat
+
+    def col2im_actbwd(self, col, Hin, Win, k, dact, dbias, out):
+        """out (NB,Hout,Wout,Cc contiguous) = fold(col) * elu'(dact); dbias += per-channel sums (pd_col2im_actbwd)."""
+        NB, Hout, Wout, Cc = out.shape
+        assert out.is_contiguous() and dact.is_contiguous() and dact.numel() == out.numel()
+        self._ck(self.lib.pd_col2im_actbwd(self.h, NB, Hin, Win, Hout, Wout, Cc, int(k), _ptr(col), _ld(col), _ptr(dact), _ptr(dbias),
+                                           _ptr(out), self._s()), "pd_col2im_actbwd")
+
     def permute4(self, inp, out, perm, accumulate=False, round_out=False):
         """out (contiguous, shape = inp.shape permuted by perm) (+)= inp.permute(perm)."""
         assert out.is_contiguous() and inp.dim() == 4

@@ -491,6 +491,62 @@ def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
     assert torch.equal(C3, C3r), f"mode 3 max diff {(C3 - C3r).abs().max().item()}"
 
 
+@pytest.mark.parametrize("M,N,K,b_mn", [(900, 48, 108, 1), (300, 96, 200, 0), (257, 40, 64, 1), (2500, 192, 96, 1), (130, 18, 40, 0)])
+def test_gemm_with_fused_elu_backward_and_bias_gradient(ops, ref, M, N, K, b_mn):
+    """pd_gemm_actbwd: C = (A B^T) * elu'(dact), dbias += column sums, in the GEMM epilogue (TMA-store staging box re-read
+    column-wise) — against GEMM + bias_act_bwd of the op table.  Integer operands: bit-exact, bias sums included."""
+    ops.set_gemm_impl(0)
+    A = ints(M, K, seed=1, lo=-2, hi=3)
+    B = ints(K, N, seed=2, lo=-2, hi=3) if b_mn else ints(N, K, seed=2, lo=-2, hi=3)
+    dact = ints(M, N, seed=3, lo=-3, hi=3)                   # elu'(y) from the output: 1 for y > 0, y + 1 otherwise
+    out = {}
+    for name, o in (("n", ops), ("r", ref)):
+        C = torch.full((M, N), float("nan"), device=DEV)
+        db = ints(N, seed=4).clone()
+        o.gemm_actbwd(A, B, C, dact, db, b_mn=bool(b_mn))
+        out[name] = (C, db)
+    assert torch.equal(out["n"][0], out["r"][0]), f"C max diff {(out['n'][0] - out['r'][0]).abs().max().item()}"
+    assert torch.equal(out["n"][1], out["r"][1]), f"dbias max diff {(out['n'][1] - out['r'][1]).abs().max().item()}"
+
+
+@pytest.mark.parametrize("NB,H,C,k,odim", [(3, 13, 96, 5, 192), (2, 30, 48, 6, 96), (7, 5, 192, 5, 1536)])
+def test_implicit_conv_input_gradient_with_fused_elu_backward(ops, ref, NB, H, C, k, odim):
+    """pd_conv_gemm_actbwd (mode 1 + ELU backward + bias gradient in the epilogue) against the composed op-table twin."""
+    ops.set_gemm_impl(0)
+    P = (H - k) // 2 + 1
+    pixels, K = NB * P * P, k * k * C
+    X = ints(NB, H, H, C, seed=1, lo=-2, hi=3)
+    Wt = ints(K, odim, seed=2, lo=-2, hi=3)                  # [K][odim]: the decoder's o_mn layout
+    dact = ints(pixels, odim, seed=3, lo=-3, hi=3)
+    out = {}
+    for name, o in (("n", ops), ("r", ref)):
+        Cm = torch.full((pixels, odim), float("nan"), device=DEV)
+        db = ints(odim, seed=4).clone()
+        o.conv_gemm_actbwd(X, k, Wt, Cm, dact, db, o_mn=True)
+        out[name] = (Cm, db)
+    assert torch.equal(out["n"][0], out["r"][0]), f"C max diff {(out['n'][0] - out['r'][0]).abs().max().item()}"
+    assert torch.equal(out["n"][1], out["r"][1]), f"dbias max diff {(out['n'][1] - out['r'][1]).abs().max().item()}"
+
+
+@pytest.mark.parametrize("NB,Hin,Cc,extra", [(3, 6, 48, 0), (2, 14, 96, 1), (5, 2, 192, 0), (2, 5, 20, 1), (70, 14, 48, 1), (3, 14, 4, 1)])
+def test_col2im_with_fused_elu_backward_and_bias_gradient(ops, ref, NB, Hin, Cc, extra):
+    """pd_col2im_actbwd (k = 4 fold of the Conv2d input gradient * elu'(saved activation), per-channel sums) against
+    col2im + bias_act_bwd of the op table; Cc = 20 takes the composed fallback (192 % (Cc / 4) != 0); `extra` rows / columns
+    past the fold (encoder: 31 = 2 * 13 + 4 + 1) receive zero gradient."""
+    k = 4
+    Hout = (Hin - 1) * 2 + k + extra                         # extra = 1: a 31-wide image whose last row / column the conv never read
+    col = ints(NB * Hin * Hin, k * k * Cc, seed=1, lo=-2, hi=3)
+    dact = ints(NB, Hout, Hout, Cc, seed=2, lo=-3, hi=3)
+    out = {}
+    for name, o in (("n", ops), ("r", ref)):
+        dst = torch.full((NB, Hout, Hout, Cc), float("nan"), device=DEV)
+        db = ints(Cc, seed=3).clone()
+        o.col2im_actbwd(col, Hin, Hin, k, dact, db, dst)
+        out[name] = (dst, db)
+    assert torch.equal(out["n"][0], out["r"][0]), f"max diff {(out['n'][0] - out['r'][0]).abs().max().item()}"
+    close(out["n"][1], out["r"][1], 1e-6, 1e-6, "bias gradient")
+
+
 @pytest.mark.parametrize("NB,Hin,k,Cc", [(3, 5, 5, 16), (2, 13, 6, 48), (5, 4, 6, 4)])
 def test_fp16_column_matrix_gemm_store_and_col2im(ops, ref, NB, Hin, k, Cc):
     """Decoder forward with fp16 column matrices: pd_gemm writes C as fp16 (PD_GEMM_C_F16) and pd_col2im / pd_col2im_imgloss

@@ -1,7 +1,8 @@
 """Reads `ncu --set full` reports (gpurun_out/*.ncu-rep or profiles/*.ncu-rep) with `ncu -i ... --page raw --csv` and writes the
 per-launch numbers the roofline discussion quotes into profiles/ncu_summary.json (bench.py reads that file for
 `roofline.traffic`; it never profiles anything itself).
-usage: python tools/ncu_summarize.py TAG=path.ncu-rep ... [--dominant TAG:index] [--out profiles/ncu_summary.json]"""
+usage: python tools/ncu_summarize.py TAG=path.ncu-rep ... [--dominant TAG:index] [--out profiles/ncu_summary.json] [--merge]
+(--merge keeps the tags already in the output file)"""
 import csv
 import io
 import json
@@ -55,6 +56,11 @@ def main():
     if "--dominant" in args:
         i = args.index("--dominant"); dominant = args[i + 1]; del args[i:i + 2]
     kernels = {}
+    if "--merge" in args:
+        args.remove("--merge")
+        if os.path.exists(out_path):
+            with open(out_path) as f:
+                kernels = json.load(f).get("kernels", {})
     for a in args:
         tag, path = a.split("=", 1)
         kernels[tag] = dict(source=os.path.basename(path), launches=read(path))
