@@ -489,6 +489,10 @@ def run_ours(args):
         timed_op("adamw", lambda p_, g, m, v, *a: 7.0 * nb(p_)),       # read p,g,m,v + write p,m,v
         timed_op("col2im", lambda col, Hin, Win, k, bias, act, out, round_out=True: nb(col, out)),
         timed_op("im2col", lambda inp, k, korder, col, round_out=True: nb(col) + float(inp.numel() * 4)),
+        # (col, Hin, Win, k, dact, dbias, out): column matrix + saved activation read, gradient image written
+        timed_op("col2im_actbwd", lambda col, Hin, Win, k, dact, dbias, out: nb(col, dact, out)),
+        timed_op("gru_fwd", lambda gi, gh, hprev, hout, *a, **k: nb(gi, gh, hprev, hout) + 4.0 * nb(hout)),   # + gates (4 D per row)
+        timed_op("ln_elu_bwd", lambda dy, x, y, *a, **k: 4.0 * nb(dy)),                                      # dy, x, y read, dx written
     ]
     step(dev_obs)
     torch.cuda.synchronize()
@@ -576,7 +580,7 @@ def run_ours(args):
                       gemm_share_of_step=gemm_ms / (ms / args.steps), gemm_flops_per_step=gemm_flops,
                       step_algorithmic_tflop=ALGO_FLOPS_ATARI / 1e12 if args.config == "atari" else None,
                       step_tflops=(ALGO_FLOPS_ATARI / 1e12) / (ms / args.steps / 1000.0) if args.config == "atari" else None,
-                      hbm_kernels=hbm_kernels[:5], hbm_peak_gbs=pk["hbm_gbs"],
+                      hbm_kernels=hbm_kernels[:8], hbm_peak_gbs=pk["hbm_gbs"],
                       ncu_summary=ncu.get("kernels")),
     )
     if rank == 0 and world == 1 and not args.no_ref_gpu:
