@@ -87,6 +87,11 @@ __device__ __forceinline__ float pd_round_if(float x, int on) { return on ? pd_t
 // ELU(alpha = 1).  exp(x) - 1 for x <= 0 without libm's expm1f (~45 instructions with branches — the GEMM epilogues that fuse
 // the activation were bound by it, r02 ncu of the conv1 GEMM): a degree-7 Taylor polynomial where exp(x) - 1 would cancel
 // (|x| < 0.25, truncation error < 4e-10) and ex2.approx elsewhere (result magnitude >= 0.22, relative error < 5e-7).
+__device__ __forceinline__ float pd_selp(float a, float b, bool p) {   // p ? a : b as ONE select: the compiler otherwise turns
+    float r;                                                            // the two-sided expressions below into a branch per element
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\tselp.f32 %0, %1, %2, q;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"((int)p));
+    return r;
+}
 __device__ __forceinline__ float pd_expm1_nonpos(float x) {
     float p = fmaf(x, 1.f / 5040.f, 1.f / 720.f);
     p = fmaf(p, x, 1.f / 120.f);
@@ -95,10 +100,12 @@ __device__ __forceinline__ float pd_expm1_nonpos(float x) {
     p = fmaf(p, x, 0.5f);
     p = fmaf(p, x, 1.f);
     p *= x;
-    const float e = __expf(x) - 1.f;
-    return x > -0.25f ? p : e;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return pd_selp(p, e - 1.f, x > -0.25f);
 }
-__device__ __forceinline__ float pd_elu(float x) { return x > 0.f ? x : pd_expm1_nonpos(x); }
+// both sides are evaluated on min(x, 0) and selected (r02 ncu of the conv1 GEMM: one BSSY / BSYNC region per element)
+__device__ __forceinline__ float pd_elu(float x) { return pd_selp(x, pd_expm1_nonpos(fminf(x, 0.f)), x > 0.f); }
 // d ELU / dx expressed through the ELU *output* y (alpha = 1): x>0 -> 1, else exp(x) = y + 1
 __device__ __forceinline__ float pd_elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
 __device__ __forceinline__ float pd_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
