@@ -33,6 +33,10 @@ int pd_create(int device_ordinal, pd_handle** out) {
     if (const char* e2 = getenv("PD_GEMM_2CTA")) h->gemm_2cta = atoi(e2);
     h->gemm_mn3 = 1;
     h->gemm_conv_k64 = 1;
+    h->gemm_conv_2cta = 1;
+    h->gemm_conv_m2 = 1;
+    if (const char* e9 = getenv("PD_GEMM_CONV_M2")) h->gemm_conv_m2 = atoi(e9);
+    if (const char* e8 = getenv("PD_GEMM_CONV_2CTA")) h->gemm_conv_2cta = atoi(e8);
     h->gemm_2cta_min_m = 384;
     h->fuse_actbwd = 1;
     if (const char* e7 = getenv("PD_B200_FUSE_ACTBWD")) h->fuse_actbwd = atoi(e7);

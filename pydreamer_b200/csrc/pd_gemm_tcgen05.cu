@@ -213,19 +213,27 @@ __device__ __forceinline__ void epi_f16_tile(const PdEpilogue& e, const CUtensor
 // (three 64 KB stages, one 4 KB store box per epilogue warp) so that the im2col operand arrives as four 8 KB boxes per
 // 64 pixels instead of eight 4 KB boxes — its TMA boxes cost ~415 clk each whatever their size up to 8 KB
 // (tools/microbench/tma_box_rate.cu; the r02 ncu of mode 2 showed exactly 4 x 415 clk per k-block).
-template <bool BIG>
+// VAR 2 (M2): pd_conv_gemm mode 1 with TWO 128-pixel tiles per weight box: one 256-pixel im2col box (32 KB) and one weight box
+// per k-block feed two MMAs (two accumulator tiles, all 512 TMEM columns): a TMA box costs ~400 clk + ~16 clk/KB, and with
+// N = 96-192 output channels the 128x128 form spent one such box per operand per 262 clk of MMA.
+template <int VAR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA3,
                     const __grid_constant__ CUtensorMap tmB3, const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int NST = BIG ? 3 : STAGES;                       // NST * STB + staging = STAGES * STAGE_BYTES + EPI_STAGING
-    constexpr int STB = BIG ? 2 * STAGE_BYTES : STAGE_BYTES;
-    constexpr int ABY = BIG ? 2 * A_BYTES : A_BYTES;
+    constexpr bool BIG = VAR == 1, M2 = VAR == 2;
+    constexpr bool ONEBUF = BIG || M2;                          // one 4 KB store box per epilogue warp
+    constexpr int NST = BIG ? 3 : (M2 ? 4 : STAGES);            // NST * STB + staging = STAGES * STAGE_BYTES + EPI_STAGING
+    constexpr int STB = BIG ? 2 * STAGE_BYTES : (M2 ? 2 * A_BYTES + B_BYTES : STAGE_BYTES);
+    constexpr int ABY = (BIG || M2) ? 2 * A_BYTES : A_BYTES;
+    constexpr int MROWS = M2 ? 2 * BM : BM;                     // output rows of one unit
+    constexpr int ACOLS = M2 ? 2 * BN : BN;                     // TMEM columns of one accumulator stage
+    constexpr int TCOLS = ACC_STAGES * ACOLS;
     constexpr int KSTEPS = (BIG ? 2 : 1) * (BK / UMMA_K);
     constexpr int GSTR = BIG ? 8192 : 4096;                     // bytes between the 32-column groups of an MN-major operand
     constexpr int KROWS = BIG ? 64 : 32;                        // k-rows (pixels) of one MN-major k-block
-    static_assert(NST * STB + EPI_WARPS * (BIG ? 1 : 2) * 4096 == STAGES * STAGE_BYTES + EPI_STAGING, "same shared-memory footprint");
+    static_assert(NST * STB + EPI_WARPS * (ONEBUF ? 1 : 2) * 4096 == STAGES * STAGE_BYTES + EPI_STAGING, "same shared-memory footprint");
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_STAGING);
@@ -250,7 +258,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(TMEM_COLS)
+                     "n"(TCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -268,7 +276,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int split = u % g.splits;
                 const int tile = u / g.splits;
-                const int m0 = (tile / g.num_n) * BM;
+                const int m0 = (tile / g.num_n) * MROWS;
                 const int n0 = (tile % g.num_n) * BN;
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
@@ -348,7 +356,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+                const uint32_t tacc = tmem_base + (uint32_t)(as * ACOLS);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -364,6 +372,8 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                                    : make_desc(sb + s * 32, 16, 1024, 2);
                         if (g.f16) tc_mma_f16(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                         else       tc_mma_tf32(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                        if (M2)    tc_mma_tf32(tacc + BN, make_desc(sa + A_BYTES + s * 32, 16, 1024, 2), bd, idesc,
+                                               (kb > kb0 || s > 0) ? 1u : 0u);     // second 128-pixel tile, same weights
                     }
                     tc_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
                     if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -382,7 +392,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int chalf = (warp - 2) >> 2;             // which of the quarter's two warps: chunks chalf, chalf + 2, ...
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
-        uint8_t* stg0 = smem + NST * STB + (warp - 2) * ((BIG ? 1 : 2) * 4096);   // BIG: one store box per warp
+        uint8_t* stg0 = smem + NST * STB + (warp - 2) * ((ONEBUF ? 1 : 2) * 4096);   // BIG / M2: one store box per warp
         const bool b_vec = e.bias && ((((uintptr_t)e.bias) & 15) == 0);
         float* stgf = reinterpret_cast<float*>(stg0);     // scalar fallback view (pitch 33 floats fits in 8 KB)
         int sbuf = 0;
@@ -390,13 +400,14 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int split = u % g.splits;
             const int tile = u / g.splits;
-            const int m0 = (tile / g.num_n) * BM;
+            const int m0 = (tile / g.num_n) * MROWS;
             const int n0 = (tile % g.num_n) * BN;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const int rbase = m0 + quarter * 32;
+          for (int sub = 0; sub < (M2 ? 2 : 1); ++sub) {                 // M2: the unit's two 128-row accumulator tiles
+            const int rbase = m0 + sub * BM + quarter * 32;
             const int row = rbase + lane;
-            const uint32_t tbase = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t tbase = tmem_base + (uint32_t)(as * ACOLS + sub * BN) + ((uint32_t)(quarter * 32) << 16);
             const bool extras = !e.accumulate || (g.extras_on_split0 && split == 0);
             const int nchunk = rbase >= g.M ? 0 : min(BN / 32, (g.N - n0 + 31) / 32);   // chunks with real columns (warp-uniform)
             if (e.c_f16) epi_f16_tile(e, &tmC, g.N, tbase, n0, rbase, nchunk, chalf, extras, stg0, sbuf);
@@ -460,7 +471,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     uint8_t* buf = stg0 + sbuf * 4096;
                     if (lane == 0) {                                                                 // buffer free again?
-                        if (BIG) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (ONEBUF) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         else     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     }
                     __syncwarp();
@@ -492,7 +503,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             sacc += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
                         if (col0 + lane < g.N) atomicAdd(e.dbias + col0 + lane, sacc);
                     }
-                    if (!BIG) sbuf ^= 1;
+                    if (!ONEBUF) sbuf ^= 1;
                 } else {
                     // generic fallback (C not TMA-addressable: ldc % 4 != 0, e.g. N = 1 / 18 outputs)
 #pragma unroll
@@ -522,6 +533,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
                 }
             }
+          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -533,7 +545,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS)
                      : "memory");
     }
 }
@@ -566,6 +578,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint32_t leade
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_2sm(const void* tmap, uint32_t leader_bar, void* smem, int c, int w, int h, int n,
+                                                    int off_w, int off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"((uint16_t)off_w), "h"((uint16_t)off_h)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t leader_bar, void* smem, int c0, int c1, int c2) {
@@ -663,8 +683,16 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     uint8_t* sb = sa + A_BYTES;
                     const uint32_t lbar = smem_u32(&full[stage]) & PEER_MASK;  // the leader's barrier collects both CTAs' bytes
                     if (leader) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
-                    const int k0 = kb * (g.f16 ? 2 * BK : BK);
-                    if (!g.a_mn) {
+                    int k0 = kb * (g.f16 ? 2 * BK : BK);
+                    if (g.a_mode == 1) {
+                        // implicit im2col rows (as in the 1-CTA kernel): this CTA's 128 pixels x 32 channels of one filter tap
+                        const int tap = kb / g.cv_cblocks, c0 = (kb - tap * g.cv_cblocks) * 32;
+                        const int kh = tap / g.cv_k, kw = tap - kh * g.cv_k;
+                        const int n_ = m0 / g.cv_PQ, r_ = m0 - n_ * g.cv_PQ;
+                        const int p_ = r_ / g.cv_Q, q_ = r_ - p_ * g.cv_Q;
+                        tma_load_im2col_2sm(&tmA, lbar, sa, c0, 2 * q_, 2 * p_, n_, kw, kh);
+                        k0 = tap * g.cv_C + c0;
+                    } else if (!g.a_mn) {
                         tma_load_2d_2sm(&tmA, lbar, sa, k0, m0);
                     } else if (mn3_ok(g.a3_on, g.a3_part, m0 >> 5)) {
                         tma_load_3d_2sm(&tmA3, lbar, sa, 0, k0, m0 >> 5);
@@ -785,6 +813,20 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = pd_elu(v[j]);
                 }
+                if (e.dact && row < g.M) {                // ELU backward of the layer below (as in the 1-CTA kernel)
+                    const float* yp = e.dact + (long)row * e.lddact + col0;
+                    if (((e.lddact & 3) == 0) && ((((uintptr_t)e.dact) & 15) == 0) && col0 + 32 <= g.N) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(yp) + j);
+                            v[4 * j] *= pd_elu_grad_from_out(q.x); v[4 * j + 1] *= pd_elu_grad_from_out(q.y);
+                            v[4 * j + 2] *= pd_elu_grad_from_out(q.z); v[4 * j + 3] *= pd_elu_grad_from_out(q.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (col0 + j < g.N) v[j] *= pd_elu_grad_from_out(__ldg(yp + j));
+                    }
+                }
                 if (e.round_out) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
@@ -810,6 +852,13 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(col0), "r"(rbase) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (e.dbias) {                            // bias gradient: column sums of the staged box (see the 1-CTA kernel)
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        sacc += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                    if (col0 + lane < g.N) atomicAdd(e.dbias + col0 + lane, sacc);
                 }
                 sbuf ^= 1;
             }
@@ -930,8 +979,9 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     PD_REQUIRE(h, (ldo % 4) == 0 && ((((uintptr_t)O) & 15) == 0), "pd_conv_gemm: operand alignment");
     PD_REQUIRE(h, (epi.ldc % 4) == 0 && ((((uintptr_t)epi.C) & 15) == 0), "pd_conv_gemm: C must be TMA-addressable");
     if (!h->gemm_smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
         h->gemm_smem_configured = 1;
     }
@@ -942,6 +992,8 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     g.cv_PQ = P * Q; g.cv_Q = Q; g.cv_C = C; g.cv_k = k; g.cv_cblocks = pd_cdiv(C, 32); g.cv_cpad = g.cv_cblocks * 32;
     // modes 2 / 3 (K = pixels): 64-pixel k-blocks, the BIG instantiation (PD_GEMM_CONV_K64=0: the 32-pixel form)
     const bool big = mode != 1 && h->gemm_conv_k64;
+    // mode 1: two 128-pixel tiles per weight box (M2 instantiation; PD_GEMM_CONV_M2=0: one, or the 2-CTA kernel)
+    const bool m2 = mode == 1 && h->gemm_conv_m2 && pixels > BM;
     const int kpix = big ? 64 : 32;
     g.mn_lbo = big ? 8192 : 4096; g.mn_sbo = 512;
     g.epi = epi; g.tma_store = 1;
@@ -953,7 +1005,7 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
         M = (int)pixels; N = ODIM;
         g.a_mode = 1; g.a_mn = 0; g.b_mode = 0; g.b_mn = o_mn;
         g.kb_total = k * k * g.cv_cblocks;
-        rc = make_im2col_map(h, &tmA, X, NB, H, W, C, k, BM, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
+        rc = make_im2col_map(h, &tmA, X, NB, H, W, C, k, m2 ? 2 * BM : BM, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
         const long Ktot = (long)k * k * C;
         if (!o_mn) rc = make_map(h, &tmB, O, (uint64_t)Ktot, (uint64_t)N, (uint64_t)ldo, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
         else       rc = make_map(h, &tmB, O, (uint64_t)N, (uint64_t)Ktot, (uint64_t)ldo, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -979,15 +1031,33 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     rc = make_map(h, &tmC, epi.C, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     g.M = M; g.N = N; g.K = 0;
-    g.num_m = pd_cdiv(M, BM); g.num_n = pd_cdiv(N, BN);
+    g.num_m = pd_cdiv(M, m2 ? 2 * BM : BM); g.num_n = pd_cdiv(N, BN);
     int tiles = g.num_m * g.num_n, splits = 1;
+    // mode 1 (K-major im2col rows) on the 2-CTA kernel: a pair covers 256 pixels x 256 output channels, each CTA gathers its own
+    // 128 pixels and half of the weight rows — fewer operand bytes per SM than two independent 128x128 tiles (a 128x128 TF32
+    // k-block is fed at ~1045 clk by one SM's TMA path against 262 clk of MMA)
+    if (mode == 1 && !m2 && h->gemm_2cta && h->gemm_conv_2cta && M >= h->gemm_2cta_min_m) {
+        const int tiles2 = pd_cdiv(M, 256) * pd_cdiv(N, BN2);
+        const int pairs_avail = h->num_sms / 2;
+        g.kb_per_split = g.kb_total; g.splits = 1;
+        const int gridp = tiles2 < pairs_avail ? tiles2 : pairs_avail;
+        if (!h->gemm2_smem_configured) {
+            cudaError_t e2 = cudaFuncSetAttribute(pd_gemm_tf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+            if (e2 != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(2cta smem=%d): %s", SMEM2_BYTES, cudaGetErrorString(e2));
+            h->gemm2_smem_configured = 1;
+        }
+        pd_gemm_tf32_2cta_kernel<<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+        PD_CHECK_LAUNCH(h, "pd_gemm_tf32_2cta_kernel(im2col)");
+        return PD_OK;
+    }
     if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, big ? 4 : 8);
     g.kb_per_split = pd_cdiv(g.kb_total, splits);
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
     int units = tiles * g.splits;
     int grid = units < h->num_sms ? units : h->num_sms;
-    if (big) pd_gemm_tf32_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
-    else     pd_gemm_tf32_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    if (big)     pd_gemm_tf32_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    else if (m2) pd_gemm_tf32_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    else         pd_gemm_tf32_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel(im2col)");
     return PD_OK;
 }
@@ -999,8 +1069,9 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
                lda, ldb);
     PD_REQUIRE(h, (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "pd_gemm(tcgen05): A/B must be 16B aligned");
     if (!h->gemm_smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
         h->gemm_smem_configured = 1;
     }
@@ -1071,7 +1142,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     if (epi.accumulate) splits = pick_splits(tiles, g.kb_total, h->num_sms, 8);   // split-K over idle SMs / partial waves
     // Large tiles-rich problems go to the 2-CTA (cta_group::2) 256x256 kernel; it needs a TMA-addressable C.
     PD_REQUIRE(h, !epi.dact || (g.tma_store && !epi.c_f16 && !epi.accumulate), "pd_gemm(actbwd): needs a TMA-addressable fp32 C");
-    int use2 = h->gemm_2cta && g.tma_store && M >= h->gemm_2cta_min_m && N >= 256 && !g.extras_on_split0 && !epi.dact;
+    int use2 = h->gemm_2cta && g.tma_store && M >= h->gemm_2cta_min_m && N >= 256 && !g.extras_on_split0;
     if (use2) {
         int tiles2 = pd_cdiv(M, 256) * pd_cdiv(N, BN2);
         int pairs_avail = h->num_sms / 2;
@@ -1098,7 +1169,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units
     int units = tiles * g.splits;
     int grid = units < h->num_sms ? units : h->num_sms;
-    pd_gemm_tf32_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    pd_gemm_tf32_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel");
     return PD_OK;
 }

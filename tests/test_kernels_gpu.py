@@ -465,7 +465,9 @@ def test_fp16_side_outputs_of_producers(ops, ref):
 
 
 @pytest.mark.parametrize("NB,H,C,k,odim", [(3, 14, 96, 4, 192), (2, 31, 48, 4, 96), (3, 13, 96, 5, 192), (2, 30, 48, 6, 96),
-                                             (5, 6, 192, 4, 384), (7, 5, 192, 5, 1536)])
+                                             (5, 6, 192, 4, 384), (7, 5, 192, 5, 1536),
+                                             # >= 384 output pixels: mode 1 runs on the 2-CTA kernel (pairs of 128-pixel tiles)
+                                             (9, 30, 48, 6, 96), (21, 14, 96, 4, 192), (40, 8, 192, 4, 384)])
 def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
     """TMA im2col-mode operands (no materialised im2col matrix): conv forward / deconv dX (mode 1, both weight layouts),
     deconv weight gradient (mode 2) and conv weight gradient (mode 3).  Integer operands: bit-exact."""
@@ -491,6 +493,43 @@ def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
     assert torch.equal(C3, C3r), f"mode 3 max diff {(C3 - C3r).abs().max().item()}"
 
 
+@pytest.mark.parametrize("env", [dict(PD_GEMM_CONV_M2="0"), dict(PD_GEMM_CONV_M2="0", PD_GEMM_CONV_2CTA="0"),
+                                 dict(PD_GEMM_CONV_K64="0", PD_GEMM_MN3="0")],
+                         ids=["mode1_on_2cta_kernel", "mode1_128x128_tiles", "k32_blocks_2d_boxes"])
+def test_implicit_conv_gemm_alternative_routes(ref, env):
+    """The routes the default handle does not take (the switches are read when a handle is created): mode 1 on the 2-CTA
+    kernel, mode 1 with plain 128x128 tiles, the K = pixels forms with 32-pixel k-blocks and 2-D boxes.  Bit-exact."""
+    import os
+    from pydreamer_b200.ops import NativeOps
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        o = NativeOps(DEV)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    o.set_round_operands(False)
+    for NB, H, C, k, odim in ((9, 30, 48, 6, 96), (21, 14, 96, 4, 192)):
+        P = (H - k) // 2 + 1
+        pixels, K, cpad = NB * P * P, k * k * C, (C + 31) // 32 * 32
+        X = ints(NB, H, H, C, seed=1, lo=-2, hi=3)
+        Wt = ints(K, odim, seed=2, lo=-2, hi=3)
+        dact = ints(pixels, odim, seed=3, lo=-3, hi=3)
+        res = {}
+        for name, oo in (("n", o), ("r", ref)):
+            Cm, db = torch.full((pixels, odim), float("nan"), device=DEV), ints(odim, seed=4).clone()
+            oo.conv_gemm_actbwd(X, k, Wt, Cm, dact, db, o_mn=True)
+            Ot = ints(pixels, odim, seed=5, lo=-2, hi=3)
+            C2, C3 = ints(k * k * cpad, odim, seed=6), ints(odim, k * k * cpad, seed=7)
+            oo.conv_gemm(2, X, k, Ot, C2); oo.conv_gemm(3, X, k, Ot, C3)
+            res[name] = (Cm, db, C2, C3)
+        for a, b_, w in zip(res["n"], res["r"], ("mode 1 + actbwd", "dbias", "mode 2", "mode 3")):
+            assert torch.equal(a, b_), f"{env} {w}: max diff {(a - b_).abs().max().item()}"
+
+
 @pytest.mark.parametrize("M,N,K,b_mn", [(900, 48, 108, 1), (300, 96, 200, 0), (257, 40, 64, 1), (2500, 192, 96, 1), (130, 18, 40, 0)])
 def test_gemm_with_fused_elu_backward_and_bias_gradient(ops, ref, M, N, K, b_mn):
     """pd_gemm_actbwd: C = (A B^T) * elu'(dact), dbias += column sums, in the GEMM epilogue (TMA-store staging box re-read
@@ -509,7 +548,8 @@ def test_gemm_with_fused_elu_backward_and_bias_gradient(ops, ref, M, N, K, b_mn)
     assert torch.equal(out["n"][1], out["r"][1]), f"dbias max diff {(out['n'][1] - out['r'][1]).abs().max().item()}"
 
 
-@pytest.mark.parametrize("NB,H,C,k,odim", [(3, 13, 96, 5, 192), (2, 30, 48, 6, 96), (7, 5, 192, 5, 1536)])
+@pytest.mark.parametrize("NB,H,C,k,odim", [(3, 13, 96, 5, 192), (2, 30, 48, 6, 96), (7, 5, 192, 5, 1536),
+                                             (9, 30, 48, 6, 96), (30, 13, 96, 5, 192)])      # the last two: 2-CTA kernel
 def test_implicit_conv_input_gradient_with_fused_elu_backward(ops, ref, NB, H, C, k, odim):
     """pd_conv_gemm_actbwd (mode 1 + ELU backward + bias gradient in the epilogue) against the composed op-table twin."""
     ops.set_gemm_impl(0)
