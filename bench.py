@@ -95,6 +95,16 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    # nvidia-smi takes about a second to come up on an 8-GPU box — longer than a 20-step timed region — so the sampler is
+    # started before the warm-up steps and begin() / end() bracket the timed region: summary() keeps the rows that
+    # arrived inside it (plus one sampling period either side; the GPU runs the same steps there).
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -109,7 +119,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
         if self.proc:
@@ -122,7 +132,9 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        for ts, *r in self.rows:
+            if self.t0 is not None and not (self.t0 - 0.12 <= ts <= (self.t1 or time.time()) + 0.12):
+                continue
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -372,11 +384,13 @@ def run_ours(args):
     n0 = model.ops.launch_count()
     step(dev_obs)                                    # first call of a shape is always launched kernel by kernel
     launches = model.ops.launch_count() - n0         # this library's kernels in one eagerly launched step
-    for _ in range(max(args.warmup, 3) - 1):
-        step(dev_obs)
-    n1 = model.ops.launch_count()
-    with ClockSampler(local) as cs:
+    with ClockSampler(local) as cs:                  # (started before the warm-up: see ClockSampler.begin)
+        for _ in range(max(args.warmup, 3) - 1):
+            step(dev_obs)
+        n1 = model.ops.launch_count()
+        cs.begin()
         ms = timed(lambda: step(dev_obs), args.steps)
+        cs.end()
     clocks = cs.summary()
     # kernels of this library that ran in the timed region: the ones launched from Python (gradient hand-over, clip, AdamW)
     # plus, per replay, the kernel nodes the step's CUDA graph re-issues (counted when it was captured)
