@@ -48,6 +48,8 @@ struct GemmArgs {
     // (tools/microbench/tma_box_rate.cu: 4 KB boxes stream at 9.9 B/clk/SM, 16 KB boxes at 25).  a3_on / b3_on: the 3-D map is
     // valid; a3_part / b3_part: index of the one partial column group (MN % 32 != 0; tiles holding it keep the 2-D boxes), or -1.
     int a3_on, b3_on, a3_part, b3_part;
+    int k2_full;               // 2-CTA K2 instantiation: number of FULL 128-byte k-chunks (K / 32 or K / 64); a stage that reaches
+                               // past them is fetched with the 2-D boxes, which clip at K
     // implicit-GEMM convolution operands (TMA im2col mode on an NHWC tensor, k x k taps, stride 2, no padding):
     //   a_mode 1: A rows = output pixels, K = (tap, channel)            (conv forward / deconv input-gradient)
     //   a_mode 2: A' rows = (tap, channel padded to 32), K = output pixels  (deconv weight gradient)
@@ -563,6 +565,7 @@ constexpr int STAGES2 = 4;
 constexpr int STAGE2_BYTES = A_BYTES + BNH * BK * 4;        // 32 KB
 constexpr int TMEM_COLS2 = ACC_STAGES * BN2;   // 512: the whole TMEM
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_STAGING;
+constexpr int SMEM2K_BYTES = 3 * 2 * STAGE2_BYTES + 1024 + 256 + EPI_STAGING / 2;   // K2: three 64 KB stages, one store box per warp
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -622,13 +625,24 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// K2: both operands K-major and fetched TWO k-blocks at a time by one 3-D box each ({128-byte k-chunk, 128 rows, 2 k-chunks} =
+// 32 KB): three 64 KB stages, one store box per epilogue warp.  OPT-IN (PD_GEMM_2CTA_K2=1): alone, the fp16 [2500,6144,2048]
+// GEMM goes from 741 to 891 TFLOP/s and [40000,400,3072] from 691 to 827, but inside the overlapped step the 230 KB footprint
+// (198 KB without) leaves no shared memory for co-resident CTAs of the other branch and the step LOSES 0.4 ms (24.30 vs 23.89);
+// with two 64 KB stages in the old footprint the gain is gone (787 vs 749 TFLOP/s, step 24.0 vs 23.9).  r02 ncu of the fp16 [2500,6144,2048] GEMM: tensor pipe 48 %
+// active with two 16 KB boxes per 64-wide k-block — the boxes, not the MMAs, set the pace (tools/microbench/tma_box_rate.cu).
+template <bool K2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA3,
                          const __grid_constant__ CUtensorMap tmB3, const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + STAGES2 * STAGE2_BYTES + EPI_STAGING);
+    constexpr int NST2 = K2 ? 3 : STAGES2;
+    constexpr int STB2 = K2 ? 2 * STAGE2_BYTES : STAGE2_BYTES;
+    constexpr int ABY2 = K2 ? 2 * A_BYTES : A_BYTES;
+    constexpr int NBUF = K2 ? 1 : 2;                            // store boxes per epilogue warp
+    uint64_t* bars = (uint64_t*)(smem + NST2 * STB2 + EPI_WARPS * NBUF * 4096);
     uint64_t* full = bars;                       // [STAGES2]   (only the leader's are waited on)
     uint64_t* empty = bars + STAGES2;            // [STAGES2]
     uint64_t* tfull = bars + 2 * STAGES2;        // [ACC_STAGES]
@@ -679,10 +693,24 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE2_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
+                    uint8_t* sa = smem + stage * STB2;
+                    uint8_t* sb = sa + ABY2;
                     const uint32_t lbar = smem_u32(&full[stage]) & PEER_MASK;  // the leader's barrier collects both CTAs' bytes
-                    if (leader) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    if (leader) mbar_expect_tx(&full[stage], 2 * STB2);
+                    if (K2) {                                                   // two k-chunks of both operands per box
+                        if (2 * kb + 2 <= g.k2_full) {
+                            tma_load_3d_2sm(&tmA3, lbar, sa, 0, m0, 2 * kb);
+                            tma_load_3d_2sm(&tmB3, lbar, sb, 0, n0, 2 * kb);
+                        } else {                                                // the stage with the partial last chunk: 2-D boxes clip at K
+                            const int kc = g.f16 ? 2 * BK : BK;
+                            tma_load_2d_2sm(&tmA, lbar, sa, 2 * kb * kc, m0);
+                            tma_load_2d_2sm(&tmA, lbar, sa + A_BYTES, (2 * kb + 1) * kc, m0);
+                            tma_load_2d_2sm(&tmB, lbar, sb, 2 * kb * kc, n0);
+                            tma_load_2d_2sm(&tmB, lbar, sb + A_BYTES, (2 * kb + 1) * kc, n0);
+                        }
+                        if (++stage == NST2) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     int k0 = kb * (g.f16 ? 2 * BK : BK);
                     if (g.a_mode == 1) {
                         // implicit im2col rows (as in the 1-CTA kernel): this CTA's 128 pixels x 32 channels of one filter tap
@@ -708,7 +736,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                         for (int j = 0; j < BNH / 32; ++j) tma_load_2d_2sm(&tmB, lbar, sb + j * 4096, n0 + j * 32, k0);
                     }
-                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    if (++stage == NST2) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -730,19 +758,21 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint32_t sa = smem_u32(smem + stage * STB2);
+                    const uint32_t sb = sa + ABY2;
 #pragma unroll
-                    for (int s = 0; s < BK / UMMA_K; ++s) {
-                        const uint64_t ad = g.a_mn ? make_desc(sa + s * 1024, g.mn_lbo, g.mn_sbo, 1)
-                                                   : make_desc(sa + s * 32, 16, 1024, 2);
-                        const uint64_t bd = g.b_mn ? make_desc(sb + s * 1024, g.mn_lbo, g.mn_sbo, 1)
-                                                   : make_desc(sb + s * 32, 16, 1024, 2);
+                    for (int s = 0; s < (K2 ? 2 : 1) * (BK / UMMA_K); ++s) {
+                        // K2: steps 0-3 read the first k-chunk tile (16 KB), steps 4-7 the second
+                        const uint32_t ko = K2 ? (uint32_t)((s >> 2) * A_BYTES + (s & 3) * 32) : (uint32_t)(s * 32);
+                        const uint64_t ad = (!K2 && g.a_mn) ? make_desc(sa + s * 1024, g.mn_lbo, g.mn_sbo, 1)
+                                                            : make_desc(sa + ko, 16, 1024, 2);
+                        const uint64_t bd = (!K2 && g.b_mn) ? make_desc(sb + s * 1024, g.mn_lbo, g.mn_sbo, 1)
+                                                            : make_desc(sb + ko, 16, 1024, 2);
                         if (g.f16) tc_mma_f16_2sm(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                         else       tc_mma_tf32_2sm(tacc, ad, bd, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
                     }
                     tc_commit_2sm(&empty[stage]);      // frees the stage in BOTH CTAs
-                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    if (++stage == NST2) { stage = 0; phase ^= 1; }
                 }
                 tc_commit_2sm(&tfull[as]);             // both CTAs' epilogues may read their accumulator halves
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
@@ -754,7 +784,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int chalf = (warp - 2) >> 2;
         int as = 0; uint32_t aphase = 0;
         const PdEpilogue& e = g.epi;
-        uint8_t* stg0 = smem + STAGES2 * STAGE2_BYTES + (warp - 2) * (2 * 4096);
+        uint8_t* stg0 = smem + NST2 * STB2 + (warp - 2) * (NBUF * 4096);
         const bool b_vec = e.bias && ((((uintptr_t)e.bias) & 15) == 0);
         int sbuf = 0;
         const bool r_vec = e.R && ((e.ldr & 3) == 0) && ((((uintptr_t)e.R) & 15) == 0);
@@ -832,7 +862,10 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     for (int j = 0; j < 32; ++j) v[j] = pd_tf32(v[j]);
                 }
                 uint8_t* buf = stg0 + sbuf * 4096;
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (lane == 0) {
+                    if (K2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
                 __syncwarp();
                 const uint32_t rowaddr = smem_u32(buf) + lane * 128;
 #pragma unroll
@@ -860,7 +893,7 @@ pd_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         sacc += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
                     if (col0 + lane < g.N) atomicAdd(e.dbias + col0 + lane, sacc);
                 }
-                sbuf ^= 1;
+                if (!K2) sbuf ^= 1;
             }
             tc_fence_before();
             __syncwarp();
@@ -920,6 +953,23 @@ int make_map3(pd_handle* h, CUtensorMap* tm, const void* base, uint64_t mn, uint
     return PD_OK;
 }
 
+// 3-D view of a K-major operand [rows][K, ld]: (one 128-byte k-chunk, rows, k-chunks) with strides (ld, 128 B), box
+// {chunk, 128 rows, 2 chunks} = two consecutive k-block tiles of the canonical SWIZZLE_128B layout in ONE TMA operation.
+int make_map3k(pd_handle* h, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t k, uint64_t ld_elems, int f16) {
+    const uint64_t chunk = f16 ? 64 : 32, esz = f16 ? 2 : 4;
+    cuuint64_t gdim[3] = {chunk, rows, k / chunk};                    // FULL chunks only (the kernel takes the tail with 2-D boxes)
+    cuuint64_t gstride[2] = {ld_elems * esz, 128};
+    cuuint32_t box[3] = {(cuuint32_t)chunk, 128, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                                   (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "cuTensorMapEncodeTiled(3-D K-major) failed (%d): rows %llu k %llu ld %llu", (int)r,
+                                   (unsigned long long)rows, (unsigned long long)k, (unsigned long long)ld_elems);
+    return PD_OK;
+}
+
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -969,6 +1019,15 @@ int pick_splits(int tiles, int kb_total, int slots, int min_kb) {
 }
 
 }  // namespace
+
+int configure_2cta(pd_handle* h) {
+    if (h->gemm2_smem_configured) return PD_OK;
+    cudaError_t e2 = cudaFuncSetAttribute(pd_gemm_tf32_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(pd_gemm_tf32_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2K_BYTES);
+    if (e2 != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(2cta smem=%d/%d): %s", SMEM2_BYTES, SMEM2K_BYTES, cudaGetErrorString(e2));
+    h->gemm2_smem_configured = 1;
+    return PD_OK;
+}
 
 // Implicit-GEMM convolution launcher.  mode 1: C[pixels, N] = im2col(X) * B   (B: [N][K] or, b_mn, [K][N]; K = (tap, c))
 //                                      mode 2: C[(tap,cpad), N] += im2col(X)^T * Bt   (Bt stored [pixels][N])
@@ -1041,12 +1100,8 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
         const int pairs_avail = h->num_sms / 2;
         g.kb_per_split = g.kb_total; g.splits = 1;
         const int gridp = tiles2 < pairs_avail ? tiles2 : pairs_avail;
-        if (!h->gemm2_smem_configured) {
-            cudaError_t e2 = cudaFuncSetAttribute(pd_gemm_tf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-            if (e2 != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(2cta smem=%d): %s", SMEM2_BYTES, cudaGetErrorString(e2));
-            h->gemm2_smem_configured = 1;
-        }
-        pd_gemm_tf32_2cta_kernel<<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+        rc = configure_2cta(h); if (rc) return rc;
+        pd_gemm_tf32_2cta_kernel<false><<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
         PD_CHECK_LAUNCH(h, "pd_gemm_tf32_2cta_kernel(im2col)");
         return PD_OK;
     }
@@ -1149,18 +1204,24 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
         if (tiles2 * 2 < pairs_avail && !epi.accumulate) use2 = 0;          // too few pair-tiles to fill the chip
         if (use2) {
             // re-box B for the half tile (128 rows per CTA) — same box as the 1-CTA kernel, so tmB is reused as is
+            // K2: both operands K-major -> two k-chunks per 3-D box (the maps travel in the tmA3 / tmB3 slots)
+            const int kchunk = f16 ? 2 * BK : BK;                          // elements per 128-byte k-chunk
+            const bool k2 = h->gemm_2cta_k2 && !a_mn && !b_mn && !epi.c_f16 && K >= 4 * kchunk;
+            if (k2) {
+                rc = make_map3k(h, &tmA3, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, f16); if (rc) return rc;
+                rc = make_map3k(h, &tmB3, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, f16); if (rc) return rc;
+                g.kb_total = pd_cdiv(K, 2 * kchunk);
+                g.k2_full = K / kchunk;
+            }
             int splits2 = 1;
-            if (epi.accumulate) splits2 = pick_splits(tiles2, g.kb_total, pairs_avail, 8);
+            if (epi.accumulate) splits2 = pick_splits(tiles2, g.kb_total, pairs_avail, k2 ? 4 : 8);
             g.kb_per_split = pd_cdiv(g.kb_total, splits2);
             g.splits = pd_cdiv(g.kb_total, g.kb_per_split);
             int units2 = tiles2 * g.splits;
             int gridp = units2 < pairs_avail ? units2 : pairs_avail;
-            if (!h->gemm2_smem_configured) {
-                cudaError_t e2 = cudaFuncSetAttribute(pd_gemm_tf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-                if (e2 != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(2cta smem=%d): %s", SMEM2_BYTES, cudaGetErrorString(e2));
-                h->gemm2_smem_configured = 1;
-            }
-            pd_gemm_tf32_2cta_kernel<<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+            rc = configure_2cta(h); if (rc) return rc;
+            if (k2) pd_gemm_tf32_2cta_kernel<true><<<gridp * 2, NUM_THREADS, SMEM2K_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+            else    pd_gemm_tf32_2cta_kernel<false><<<gridp * 2, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
             PD_CHECK_LAUNCH(h, "pd_gemm_tf32_2cta_kernel");
             return PD_OK;
         }

@@ -55,6 +55,8 @@ GEMM_SHAPES = [(128, 128, 32), (128, 128, 256), (50, 1000, 1024), (300, 6144, 10
                (160, 96, 200),
                # M in [384, 512): 2-CTA kernel with a quarter of the second 256-row tile past the end
                (400, 512, 96), (450, 300, 64),
+               # 2-CTA kernel with K-major operands fetched two 32-wide k-chunks per box: odd chunk count, partial last chunk
+               (1024, 512, 160), (2500, 768, 1000), (1100, 300, 136),
                # large enough for the 2-CTA (cta_group::2) 256x256 kernel when PD_GEMM_2CTA=1
                (1024, 512, 256), (2500, 6144, 96), (640, 1000, 1000)]
 
@@ -423,7 +425,9 @@ def test_optimizer_kernels_against_torch_adamw(ops):
     close(p, pt.detach(), 1e-5, 1e-6, "adamw params after 3 steps")
 
 
-@pytest.mark.parametrize("M,N,K", [(50, 1000, 1024), (2500, 400, 3072), (2500, 6144, 1000), (640, 1000, 1000), (128, 128, 64)])
+@pytest.mark.parametrize("M,N,K", [(50, 1000, 1024), (2500, 400, 3072), (2500, 6144, 1000), (640, 1000, 1000), (128, 128, 64),
+                                   # 2-CTA kernel, two k-chunks per TMA box: K with a partial last chunk / an odd chunk count
+                                   (2500, 512, 400), (2500, 1000, 2048), (1500, 768, 328), (1024, 1024, 200)])
 def test_gemm_f16_operands_exact_on_integers(ops, ref, M, N, K):
     """kind::f16 path (forward-only layers): integer operands are exact in fp16, fp32 accumulation is exact."""
     if DEV == "cpu":
@@ -440,6 +444,36 @@ def test_gemm_f16_operands_exact_on_integers(ops, ref, M, N, K):
     ops.gemm_f16(big[:, 8:8 + K], B.half(), C, act=1)                  # strided fp16 view + ELU epilogue
     ref.gemm(A, B, Cr, act=1)
     close(C, Cr, 1e-6, 1e-6, "f16 strided")
+
+
+def test_gemm_2cta_two_k_chunks_per_box_route(ref):
+    """The opt-in K2 instantiation of the 2-CTA kernel (PD_GEMM_2CTA_K2=1, read when a handle is created): both operands K-major,
+    two 128-byte k-chunks per 3-D TMA box, the stage holding a partial last chunk fetched with 2-D boxes.  Bit-exact."""
+    import os
+    from pydreamer_b200.ops import NativeOps
+    old = os.environ.get("PD_GEMM_2CTA_K2")
+    os.environ["PD_GEMM_2CTA_K2"] = "1"
+    try:
+        o = NativeOps(DEV)
+    finally:
+        if old is None:
+            os.environ.pop("PD_GEMM_2CTA_K2", None)
+        else:
+            os.environ["PD_GEMM_2CTA_K2"] = old
+    o.set_round_operands(False)
+    for M, N, K in ((2500, 512, 400), (2500, 1000, 2048), (1500, 768, 328), (2500, 6144, 1000)):      # fp16 operands
+        A, B = ints(M, K, seed=1), ints(N, K, seed=2)
+        bias, res = ints(N, seed=3), ints(M, N, seed=4)
+        C, Cr = torch.full((M, N), float("nan"), device=DEV), torch.empty(M, N, device=DEV)
+        o.gemm_f16(A.half(), B.half(), C, bias=bias, res=res)
+        ref.gemm(A, B, Cr, bias=bias, res=res)
+        assert torch.equal(C, Cr), f"f16 {M, N, K}: max diff {(C - Cr).abs().max().item()}"
+    for M, N, K in ((1024, 512, 160), (2500, 768, 1000), (1100, 300, 136), (2500, 400, 3072)):       # tf32 operands
+        A, B = ints(M, K, seed=1), ints(N, K, seed=2)
+        C, Cr = torch.full((M, N), float("nan"), device=DEV), torch.empty(M, N, device=DEV)
+        o.gemm(A, B, C)
+        ref.gemm(A, B, Cr)
+        assert torch.equal(C, Cr), f"tf32 {M, N, K}: max diff {(C - Cr).abs().max().item()}"
 
 
 def test_fp16_side_outputs_of_producers(ops, ref):
