@@ -38,6 +38,14 @@ constexpr int EPI_WARPS = 8;                   // two warps per TMEM lane quarte
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_STAGING = EPI_WARPS * 2 * 4096;   // per epilogue warp: two 32x32 fp32 swizzled TMA-store boxes
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGING;
+// Ring depth of the plain 128x128 instantiation.  -DPD_GEMM_STAGES0=4 (197 KB instead of 229 KB of shared memory, room for
+// co-resident CTAs of the step's other branch) was measured against 5 on one box: 23.94 / 23.92 vs 23.94 / 23.94 ms per step —
+// no difference either way, so the deeper ring stays.
+#ifndef PD_GEMM_STAGES0
+#define PD_GEMM_STAGES0 5
+#endif
+constexpr int STAGES0 = PD_GEMM_STAGES0;
+constexpr int SMEM0_BYTES = STAGES0 * STAGE_BYTES + 1024 + 256 + EPI_STAGING;
 
 struct GemmArgs {
     int M, N, K;
@@ -226,7 +234,7 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     constexpr bool BIG = VAR == 1, M2 = VAR == 2;
     constexpr bool ONEBUF = BIG || M2;                          // one 4 KB store box per epilogue warp
-    constexpr int NST = BIG ? 3 : (M2 ? 4 : STAGES);            // NST * STB + staging = STAGES * STAGE_BYTES + EPI_STAGING
+    constexpr int NST = BIG ? 3 : (M2 ? 4 : STAGES0);           // BIG / M2: NST * STB + staging = STAGES * STAGE_BYTES + EPI_STAGING
     constexpr int STB = BIG ? 2 * STAGE_BYTES : (M2 ? 2 * A_BYTES + B_BYTES : STAGE_BYTES);
     constexpr int ABY = (BIG || M2) ? 2 * A_BYTES : A_BYTES;
     constexpr int MROWS = M2 ? 2 * BM : BM;                     // output rows of one unit
@@ -235,10 +243,10 @@ pd_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int KSTEPS = (BIG ? 2 : 1) * (BK / UMMA_K);
     constexpr int GSTR = BIG ? 8192 : 4096;                     // bytes between the 32-column groups of an MN-major operand
     constexpr int KROWS = BIG ? 64 : 32;                        // k-rows (pixels) of one MN-major k-block
-    static_assert(NST * STB + EPI_WARPS * (ONEBUF ? 1 : 2) * 4096 == STAGES * STAGE_BYTES + EPI_STAGING, "same shared-memory footprint");
+    static_assert(VAR == 0 || NST * STB + EPI_WARPS * (ONEBUF ? 1 : 2) * 4096 == STAGES * STAGE_BYTES + EPI_STAGING, "shared-memory footprint");
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_STAGING);
+    uint64_t* bars = (uint64_t*)(smem + NST * STB + EPI_WARPS * (ONEBUF ? 1 : 2) * 4096);
     uint64_t* full = bars;                       // [STAGES]
     uint64_t* empty = bars + STAGES;             // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;         // [ACC_STAGES]
@@ -627,9 +635,9 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 
 // K2: both operands K-major and fetched TWO k-blocks at a time by one 3-D box each ({128-byte k-chunk, 128 rows, 2 k-chunks} =
 // 32 KB): three 64 KB stages, one store box per epilogue warp.  OPT-IN (PD_GEMM_2CTA_K2=1): alone, the fp16 [2500,6144,2048]
-// GEMM goes from 741 to 891 TFLOP/s and [40000,400,3072] from 691 to 827, but inside the overlapped step the 230 KB footprint
-// (198 KB without) leaves no shared memory for co-resident CTAs of the other branch and the step LOSES 0.4 ms (24.30 vs 23.89);
-// with two 64 KB stages in the old footprint the gain is gone (787 vs 749 TFLOP/s, step 24.0 vs 23.9).  r02 ncu of the fp16 [2500,6144,2048] GEMM: tensor pipe 48 %
+// GEMM goes from 741 to 891 TFLOP/s and [40000,400,3072] from 691 to 827, but the overlapped step LOSES 0.4 ms (24.30 vs 23.89,
+// same box, twice) although its serialised phases get shorter (dream 6.79 vs 6.96 ms); with two 64 KB stages in the old 198 KB
+// footprint the kernel-level gain is gone (787 vs 749 TFLOP/s, step 24.0 vs 23.9).  Not understood; left off.  r02 ncu of the fp16 [2500,6144,2048] GEMM: tensor pipe 48 %
 // active with two 16 KB boxes per 64-wide k-block — the boxes, not the MMAs, set the pace (tools/microbench/tma_box_rate.cu).
 template <bool K2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -1038,7 +1046,7 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     PD_REQUIRE(h, (ldo % 4) == 0 && ((((uintptr_t)O) & 15) == 0), "pd_conv_gemm: operand alignment");
     PD_REQUIRE(h, (epi.ldc % 4) == 0 && ((((uintptr_t)epi.C) & 15) == 0), "pd_conv_gemm: C must be TMA-addressable");
     if (!h->gemm_smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM0_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
@@ -1112,7 +1120,7 @@ int pd_conv_gemm_launch(pd_handle* h, int mode, int NB, int H, int W, int C, int
     int grid = units < h->num_sms ? units : h->num_sms;
     if (big)     pd_gemm_tf32_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     else if (m2) pd_gemm_tf32_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
-    else         pd_gemm_tf32_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    else         pd_gemm_tf32_kernel<0><<<grid, NUM_THREADS, SMEM0_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel(im2col)");
     return PD_OK;
 }
@@ -1124,7 +1132,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
                lda, ldb);
     PD_REQUIRE(h, (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "pd_gemm(tcgen05): A/B must be 16B aligned");
     if (!h->gemm_smem_configured) {
-        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM0_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pd_gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) PD_FAIL(h, PD_ERR_DEVICE, "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
@@ -1230,7 +1238,7 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units
     int units = tiles * g.splits;
     int grid = units < h->num_sms ? units : h->num_sms;
-    pd_gemm_tf32_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+    pd_gemm_tf32_kernel<0><<<grid, NUM_THREADS, SMEM0_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
     PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel");
     return PD_OK;
 }
