@@ -46,6 +46,10 @@ __device__ __forceinline__ void tma_box(const CUtensorMap* map, uint64_t* bar, v
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(s_u32(dst)), "l"((uint64_t)map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_box3(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(s_u32(dst)), "l"((uint64_t)map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -161,6 +165,12 @@ struct Job {
     const CUtensorMap* xmap[2];
     int nx, xrow0, xrows, xf16;
     int kcol0, nkb, x2_from;
+    // Grouped weight boxes (ngop > 0): the SAME ntile tiles fetched by a few larger TMA operations instead of one 2 KB box per
+    // tile — op o fills tiles gdst[o].. from rows grow[o].. of gmap[o]; g3d[o]: a 3-D map (k, row within gate, gate) whose box
+    // spans all gates (tools/microbench/tma_box_rate.cu: small boxes cost almost as much as large ones).
+    int ngop;
+    const CUtensorMap* gmap[3];
+    int grow[3], gdst[3], g3d[3];
 };
 template <int MAXT>
 __device__ __forceinline__ bool job_needs_x2(const Job<MAXT>& j, int kb) { return j.nx == 2 && j.kcol0 + (kb + 1) * KB > j.x2_from; }
@@ -180,6 +190,13 @@ __device__ void produce(Ring<MAXT, XB>& ring, const Job<MAXT>& j, const unsigned
         mbar_wait(ring.empty + n % NSTAGE, ((n / NSTAGE) & 1) ^ 1);
         mbar_expect_tx(ring.full + n % NSTAGE, job_bytes(j, kb));
         uint8_t* st = ring.stage(n);
+        if (j.ngop > 0) {
+            for (int o = 0; o < j.ngop; ++o) {
+                if (j.g3d[o]) tma_box3(j.gmap[o], ring.full + n % NSTAGE, st + j.gdst[o] * A_TILE, j.kcol0 + kb * KB, j.grow[o], 0);
+                else          tma_box(j.gmap[o], ring.full + n % NSTAGE, st + j.gdst[o] * A_TILE, j.kcol0 + kb * KB, j.grow[o]);
+            }
+            return;
+        }
         for (int i = 0; i < j.ntile; ++i) tma_box(j.wmap[i], ring.full + n % NSTAGE, st + i * A_TILE, j.kcol0 + kb * KB, j.row0[i]);
     };
     auto xboxes = [&](int kb) {
@@ -411,6 +428,22 @@ inline int make_map(pd_handle* h, const char* who, CUtensorMap* tm, const void* 
                                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "%s: cuTensorMapEncodeTiled failed (%d) for [%ld, %d]", who, (int)r, rows, K);
+    return PD_OK;
+}
+
+// [gates * rows_per_gate, K] fp16 weight matrix as a 3-D map (k, row within gate, gate): one box {64 halfs, box_rows, gates}
+// lands in shared memory gate after gate — the tiles of all gates for one block of rows in ONE TMA operation.
+inline int make_map3g(pd_handle* h, const char* who, CUtensorMap* tm, const void* base, long rows_per_gate, int K, int gates,
+                      int box_rows) {
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows_per_gate, (cuuint64_t)gates};
+    cuuint64_t gstride[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows_per_gate * K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)gates};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, gdim, gstride, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PD_FAIL(h, PD_ERR_ARG, "%s: cuTensorMapEncodeTiled(3-D gates) failed (%d) for [%d x %ld, %d]", who, (int)r,
+                                   gates, rows_per_gate, K);
     return PD_OK;
 }
 

@@ -87,26 +87,26 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_bwd_kernel(const pd_rssm_bw
     const int kslice2 = Z / KS2, kslice6 = D3 / KS6;
 
     auto job_p2 = [&](int t) {
-        JobB j; j.xf16 = 0; j.ntile = nt2; j.nx = 1; j.xmap[0] = &maps.dpost; j.xmap[1] = &maps.dpost; j.xrow0 = t * BI; j.xrows = BROWS;
+        JobB j; j.ngop = 0; j.xf16 = 0; j.ntile = nt2; j.nx = 1; j.xmap[0] = &maps.dpost; j.xmap[1] = &maps.dpost; j.xrow0 = t * BI; j.xrows = BROWS;
         j.kcol0 = ks2 * kslice2; j.nkb = nt2 ? (kslice2 + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wpmT; j.row0[i] = f2_0 + 16 * i; }
         return j;
     };
     auto job_p4 = [&](int t) {
-        JobB j; j.xf16 = 0; j.ntile = nu4 > 0 ? 1 : 0; j.nx = 1; j.xmap[0] = &maps.dy2; j.xmap[1] = &maps.dy2; j.xrow0 = t * BI; j.xrows = BROWS;
+        JobB j; j.ngop = 0; j.xf16 = 0; j.ntile = nu4 > 0 ? 1 : 0; j.nx = 1; j.xmap[0] = &maps.dy2; j.xmap[1] = &maps.dy2; j.xrow0 = t * BI; j.xrows = BROWS;
         j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wphT; j.row0[i] = u4_0; }
         return j;
     };
     auto job_p6 = [&](int t) {
-        JobB j; j.xf16 = 0; j.ntile = (nt6h || nt6z) ? 6 : 0; j.nx = 2; j.xmap[0] = &maps.dgh; j.xmap[1] = &maps.dgi; j.xrow0 = t * BI; j.xrows = BROWS;
+        JobB j; j.ngop = 0; j.xf16 = 0; j.ntile = (nt6h || nt6z) ? 6 : 0; j.nx = 2; j.xmap[0] = &maps.dgh; j.xmap[1] = &maps.dgi; j.xrow0 = t * BI; j.xrows = BROWS;
         j.kcol0 = ks6 * kslice6; j.nkb = j.ntile ? (kslice6 + KB - 1) / KB : 0; j.x2_from = 2 * D;   // dgi == dgh for the r, u gates
         for (int i = 0; i < 4; ++i) { j.wmap[i] = &maps.whhT; j.row0[i] = u6_0 + 16 * i; }
         for (int i = 0; i < 2; ++i) { j.wmap[4 + i] = &maps.wihT; j.row0[4 + i] = f6_0 + 16 * i; }
         return j;
     };
     auto job_p9 = [&](int t) {
-        JobB j; j.xf16 = 0; j.ntile = in9 ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = &maps.dx1_16; j.xmap[1] = &maps.dx1_16;
+        JobB j; j.ngop = 0; j.xf16 = 0; j.ntile = in9 ? (C + 15) / 16 : 0; j.nx = 1; j.xmap[0] = &maps.dx1_16; j.xmap[1] = &maps.dx1_16;
         j.xrow0 = t * BI + b9_0; j.xrows = 16;
         j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wzT; j.row0[i] = g9 * C + 16 * i; }

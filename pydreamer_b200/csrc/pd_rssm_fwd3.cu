@@ -53,6 +53,10 @@ struct FwdMaps {
     CUtensorMap za, h;                         // fp16 activations [BI, K], box {64 halfs, 64 rows}
     CUtensorMap pin16;                         // fp16 [BI, Hd], box {64 halfs, 16 rows}
     CUtensorMap pin64;                         // the same matrix, box {64 halfs, 64 rows} (MULTI phase D)
+    // grouped weight boxes: all three gates of a row block in one 3-D box, the 32 consecutive rows of W_ph / W_pm in one 2-D box
+    CUtensorMap wih3;                          // W_ih as (k, unit, gate): box {64 halfs, 16 units, 3 gates} = tiles 0..2 of phase B
+    CUtensorMap whh3;                          // W_hh as (k, unit, gate): box {64 halfs, 64 units, 3 gates} = tiles 0..11 of phase C
+    CUtensorMap wph32, wpm32;                  // box {64 halfs, 32 rows} = tiles 12, 13 of phase C / the two class tiles of phase D
 };
 
 // LayerNorm + ELU of one row held as v[4] per consumer thread (features tid + 256 i); writes fp32 (fp16-representable) and
@@ -85,7 +89,7 @@ __device__ void ln_elu_row(float (&v)[4], int N, const float* __restrict__ gamma
 
 template <bool MULTI>
 __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_fwd_args a, const __grid_constant__ FwdMaps maps,
-                                                                 const int KS) {
+                                                                 const int KS, const int GW) {
     constexpr int TMEM_COLS = MULTI ? 512 : 128;
     constexpr int HS = MULTI ? HB : BROWS;                  // row stride of hcs
     constexpr int DR = MULTI ? 64 : 16;                     // batch rows of one phase-D pass
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         JobF j; j.ntile = nu > 0 ? 3 : 0; j.nx = 1; j.xmap[0] = &maps.za; j.xmap[1] = &maps.za; j.xrow0 = 0; j.xrows = BROWS; j.xf16 = 1;
         j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wih; j.row0[i] = (i % 3) * D + u4_0; }
+        j.ngop = GW ? 1 : 0; j.gmap[0] = &maps.wih3; j.grow[0] = u4_0; j.gdst[0] = 0; j.g3d[0] = 1;
         return j;
     };
     auto job_c = [&]() {
@@ -151,6 +156,9 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         j.kcol0 = ks * kslice; j.nkb = j.ntile ? (kslice + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < 12; ++i) { j.wmap[i] = &maps.whh; j.row0[i] = (i / 4) * D + u6_0 + 16 * (i % 4); }   // tile = gate * 4 + i
         for (int i = 0; i < 2; ++i) { j.wmap[12 + i] = &maps.wph; j.row0[12 + i] = f6_0 + 16 * i; }
+        j.ngop = GW ? 2 : 0;
+        j.gmap[0] = &maps.whh3; j.grow[0] = u6_0; j.gdst[0] = 0; j.g3d[0] = 1;
+        j.gmap[1] = &maps.wph32; j.grow[1] = f6_0; j.gdst[1] = 12; j.g3d[1] = 0;
         return j;
     };
     auto job_d = [&]() {
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(NT, 1) rssm_unroll_fwd3_kernel(const pd_rssm_f
         j.xrow0 = b9_0; j.xrows = DR;
         j.xf16 = 1; j.kcol0 = 0; j.nkb = j.ntile ? (Hd + KB - 1) / KB : 0; j.x2_from = 1 << 30;
         for (int i = 0; i < MAXT; ++i) { j.wmap[i] = &maps.wpm; j.row0[i] = g9 * C + 16 * i; }
+        j.ngop = (GW && j.ntile == 2) ? 1 : 0; j.gmap[0] = &maps.wpm32; j.grow[0] = g9 * C; j.gdst[0] = 0; j.g3d[0] = 0;
         return j;
     };
 
@@ -483,12 +492,18 @@ extern "C" int pd_rssm_unroll_fwd(pd_handle* h, const pd_rssm_fwd_args* a, void*
     if (!rc) rc = make_map(h, who, &maps.h, a->ws_h16, a->BI, a->D, BROWS, true);
     if (!rc) rc = make_map(h, who, &maps.pin16, a->ws_pin16, a->BI, a->Hd, 16, true);
     if (!rc) rc = make_map(h, who, &maps.pin64, a->ws_pin16, a->BI, a->Hd, BROWS, true);
+    if (!rc) rc = make_map3g(h, who, &maps.wih3, a->w_ih16, a->D, a->Hd, 3, 16);
+    if (!rc) rc = make_map3g(h, who, &maps.whh3, a->w_hh16, a->D, a->D, 3, 64);
+    if (!rc) rc = make_map(h, who, &maps.wph32, a->w_ph16, a->Hd, a->D, 32, true);
+    if (!rc) rc = make_map(h, who, &maps.wpm32, a->w_pm16, Z, a->Hd, 32, true);
     if (rc) return rc;
     if (cudaMemsetAsync(a->ws_barrier, 0, 16 * sizeof(unsigned), s) != cudaSuccess)
         PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: memset failed");
     pd_rssm_fwd_args args = *a;
+    const char* gwe = getenv("PD_B200_K1_GROUPED_W");           // grouped weight boxes unless PD_B200_K1_GROUPED_W=0
+    int gwv = (gwe && atoi(gwe) == 0) ? 0 : 1;
     int ksv = KS;
-    void* kargs[] = {(void*)&args, (void*)&maps, (void*)&ksv};
+    void* kargs[] = {(void*)&args, (void*)&maps, (void*)&ksv, (void*)&gwv};
     const void* fn = multi ? (const void*)rssm_unroll_fwd3_kernel<true> : (const void*)rssm_unroll_fwd3_kernel<false>;
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(P), dim3(NT), kargs, SMEM_REQ, s);
     if (e != cudaSuccess) PD_FAIL(h, PD_ERR_LAUNCH, "pd_rssm_unroll_fwd: %s", cudaGetErrorString(e));
