@@ -35,6 +35,8 @@ int pd_create(int device_ordinal, pd_handle** out) {
     h->gemm_conv_k64 = 1;
     h->gemm_conv_2cta = 1;
     h->gemm_conv_m2 = 1;
+    h->gemm_plain_m2 = 0;
+    if (const char* e11 = getenv("PD_GEMM_PLAIN_M2")) h->gemm_plain_m2 = atoi(e11);
     h->gemm_2cta_k2 = 0;
     if (const char* e10 = getenv("PD_GEMM_2CTA_K2")) h->gemm_2cta_k2 = atoi(e10);
     if (const char* e9 = getenv("PD_GEMM_CONV_M2")) h->gemm_conv_m2 = atoi(e9);

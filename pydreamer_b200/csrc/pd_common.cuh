@@ -26,6 +26,7 @@ struct pd_handle {
     int gemm_2cta_min_m;      // smallest M that goes to the 2-CTA kernel (PD_GEMM_2CTA_MINM, default 384: three of four 128-row tiles real)
     int fuse_actbwd;          // ELU backward + bias gradient inside the producing GEMM / col2im (PD_B200_FUSE_ACTBWD=0: separate pass)
     int gemm_2cta_k2;         // 2-CTA kernel, K-major operands: two k-chunks per 3-D TMA box (opt-in: PD_GEMM_2CTA_K2=1)
+    int gemm_plain_m2;        // tall plain GEMMs with N <= 128 on the M2 instantiation (opt-in PD_GEMM_PLAIN_M2=1 / 2: faster alone, step 23.99 vs 23.90 ms)
     int gemm_conv_m2;         // pd_conv_gemm mode 1: two 128-pixel tiles per weight box (PD_GEMM_CONV_M2=0 disables)
     int gemm_conv_2cta;       // pd_conv_gemm mode 1 on the 2-CTA kernel (PD_GEMM_CONV_2CTA=0: 1-CTA 128x128 tiles)
     int gemm_conv_k64;        // pd_conv_gemm modes 2 / 3 with 64-pixel k-blocks (PD_GEMM_CONV_K64=0: 32)

@@ -1234,6 +1234,23 @@ int pd_gemm_tcgen05_launch(pd_handle* h, int M, int N, int K, const void* A, lon
             return PD_OK;
         }
     }
+    // Tall GEMMs with one n-tile (N <= 128: the 3-channel conv layers' column forms): two 128-row tiles per B box, like mode 1
+    // of the convolutions (M2 instantiation: one 256-row A box + one B box feed two MMAs).
+    // OPT-IN: alone the MN-major-B case gains, inside the step it does not (23.99 / 23.99 vs 23.90 / 23.92 ms, same box).
+    // (gemm_plain_m2: 1 = only with MN-major B — [2250000,48,108] 0.434 -> 0.312 ms; 2 = also K-major B, where the single store
+    //  box per warp costs the ELU-heavy [2402500,48,48] conv1 GEMM more than the shared B box saves: 0.197 -> 0.248 ms)
+    if (h->gemm_plain_m2 && (b_mn || h->gemm_plain_m2 > 1) && !f16 && !a_mn && N <= BN && M >= 32 * BM && splits == 1 &&
+        !epi.accumulate && g.tma_store && !epi.c_f16) {
+        rc = make_map(h, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 2 * BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        g.num_m = pd_cdiv(M, 2 * BM);
+        g.kb_per_split = g.kb_total; g.splits = 1;
+        const int units2 = g.num_m * g.num_n;
+        const int grid2 = units2 < h->num_sms ? units2 : h->num_sms;
+        pd_gemm_tf32_kernel<2><<<grid2, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmA3, tmB3, g);
+        PD_CHECK_LAUNCH(h, "pd_gemm_tf32_kernel(M2)");
+        return PD_OK;
+    }
     g.kb_per_split = pd_cdiv(g.kb_total, splits);
     g.splits = pd_cdiv(g.kb_total, g.kb_per_split);   // no empty units
     int units = tiles * g.splits;

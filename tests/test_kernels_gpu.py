@@ -57,6 +57,8 @@ GEMM_SHAPES = [(128, 128, 32), (128, 128, 256), (50, 1000, 1024), (300, 6144, 10
                (400, 512, 96), (450, 300, 64),
                # 2-CTA kernel with K-major operands fetched two 32-wide k-chunks per box: odd chunk count, partial last chunk
                (1024, 512, 160), (2500, 768, 1000), (1100, 300, 136),
+               # tall with one n-tile: two 128-row tiles per B box (M2 instantiation, M >= 4096)
+               (4500, 48, 48), (5000, 108, 40), (4200, 128, 200),
                # large enough for the 2-CTA (cta_group::2) 256x256 kernel when PD_GEMM_2CTA=1
                (1024, 512, 256), (2500, 6144, 96), (640, 1000, 1000)]
 
@@ -528,8 +530,8 @@ def test_implicit_conv_gemm_tma_im2col_exact(ops, ref, NB, H, C, k, odim):
 
 
 @pytest.mark.parametrize("env", [dict(PD_GEMM_CONV_M2="0"), dict(PD_GEMM_CONV_M2="0", PD_GEMM_CONV_2CTA="0"),
-                                 dict(PD_GEMM_CONV_K64="0", PD_GEMM_MN3="0")],
-                         ids=["mode1_on_2cta_kernel", "mode1_128x128_tiles", "k32_blocks_2d_boxes"])
+                                 dict(PD_GEMM_CONV_K64="0", PD_GEMM_MN3="0"), dict(PD_GEMM_PLAIN_M2="2")],
+                         ids=["mode1_on_2cta_kernel", "mode1_128x128_tiles", "k32_blocks_2d_boxes", "plain_m2_all_layouts"])
 def test_implicit_conv_gemm_alternative_routes(ref, env):
     """The routes the default handle does not take (the switches are read when a handle is created): mode 1 on the 2-CTA
     kernel, mode 1 with plain 128x128 tiles, the K = pixels forms with 32-pixel k-blocks and 2-D boxes.  Bit-exact."""
@@ -562,9 +564,18 @@ def test_implicit_conv_gemm_alternative_routes(ref, env):
             res[name] = (Cm, db, C2, C3)
         for a, b_, w in zip(res["n"], res["r"], ("mode 1 + actbwd", "dbias", "mode 2", "mode 3")):
             assert torch.equal(a, b_), f"{env} {w}: max diff {(a - b_).abs().max().item()}"
+    for M, N, K, b_mn in ((4500, 48, 48, 0), (5000, 108, 40, 1), (4200, 128, 200, 0)):          # tall plain GEMMs (M2 when enabled)
+        A = ints(M, K, seed=1)
+        B = ints(K, N, seed=2) if b_mn else ints(N, K, seed=2)
+        bias = ints(N, seed=3)
+        C, Cr = torch.full((M, N), float("nan"), device=DEV), torch.empty(M, N, device=DEV)
+        o.gemm(A, B, C, b_mn=bool(b_mn), bias=bias, act=1)
+        ref.gemm(A, B, Cr, b_mn=bool(b_mn), bias=bias, act=1)
+        close(C, Cr, 1e-6, 1e-6, f"{env} tall gemm {M, N, K, b_mn}")
 
 
-@pytest.mark.parametrize("M,N,K,b_mn", [(900, 48, 108, 1), (300, 96, 200, 0), (257, 40, 64, 1), (2500, 192, 96, 1), (130, 18, 40, 0)])
+@pytest.mark.parametrize("M,N,K,b_mn", [(900, 48, 108, 1), (300, 96, 200, 0), (257, 40, 64, 1), (2500, 192, 96, 1), (130, 18, 40, 0),
+                                        (4300, 48, 108, 1), (4100, 96, 64, 0)])       # the last two: M2 instantiation
 def test_gemm_with_fused_elu_backward_and_bias_gradient(ops, ref, M, N, K, b_mn):
     """pd_gemm_actbwd: C = (A B^T) * elu'(dact), dbias += column sums, in the GEMM epilogue (TMA-store staging box re-read
     column-wise) — against GEMM + bias_act_bwd of the op table.  Integer operands: bit-exact, bias sums included."""
